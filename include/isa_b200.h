@@ -1,0 +1,83 @@
+/* isa_b200.h -- C ABI of libisa_sm100.so: the B200 (sm_100a) kernels of the per-pixel
+ * instance-embedding hot path of Snoworday/instance-segmentation-attention.
+ *
+ * Conventions (they mirror the reference's one native op, the vendored SRU
+ * autograd.Function that launches precompiled kernels on raw data_ptr()s:
+ * /root/reference/code/lib/archs/modules/sru/cuda_functional.py:441-547):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its
+ *     name starts with h_ ; all tensors are dense and contiguous in the stated order;
+ *   - the caller owns every buffer, outputs and workspace included (size queries:
+ *     isa_*_workspace_bytes); the library keeps no state between calls;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising unless stated;
+ *   - return value: 0 = ok, <0 = rejected argument (ISA_ERR_*), >0 = a cudaError_t;
+ *     isa_last_error() gives the message for the calling thread;
+ *   - there is no CPU fallback: without a compute-capability-10.x device every
+ *     compute entry point fails.
+ */
+#ifndef ISA_B200_H_
+#define ISA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISA_ERR_BAD_ARG (-1)
+#define ISA_ERR_UNSUPPORTED (-2)
+#define ISA_ERR_WORKSPACE (-3)
+
+typedef void* isa_stream_t; /* cudaStream_t */
+
+const char* isa_last_error(void);
+int isa_version(void);
+int isa_num_sms(int* out);
+
+/* ------------------------------------------------------------------ discriminative loss
+ * Replaces DiscriminativeLoss.forward + autograd backward:
+ *   /root/reference/code/lib/losses/discriminative.py:162-188 (composite), :191-213 (class),
+ *   :7-62 means, :65-95 variance, :98-132 distance, :135-147 regulariser, :149-160 q-regulariser.
+ * emb        [bs][C][H][W] f32 (the NCHW tensor the network emits; no permute needed)
+ * target     kind 0: u8 label map [bs][H][W], 255 = background (1 B/pixel)
+ *            kind 1/2/3: dense masks [bs][K][H][W] as f32 / i64 / u8 (one-hot or soft),
+ *            i.e. exactly what the reference's collate hands over (lib/dataset.py:354-376)
+ * n_objects  [bs] i32 (device)
+ * w_*        weights of the four terms; the shipped composite is (1, 0, 0, 0.005)
+ * out_loss [1], out_terms [4] = unweighted (var, dist, reg, qreg), out_means [bs][K][C]
+ * workspace  isa_disc_loss_workspace_bytes(bs,C,K) bytes; hand the SAME buffer, untouched,
+ *            to isa_disc_loss_bwd (it carries the per-instance sums saved for backward).
+ */
+#define ISA_TGT_LABEL_U8 0
+#define ISA_TGT_DENSE_F32 1
+#define ISA_TGT_DENSE_I64 2
+#define ISA_TGT_DENSE_U8 3
+
+size_t isa_disc_loss_workspace_bytes(int bs, int C, int K);
+
+int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, const int* n_objects,
+                      int bs, int C, int H, int W, int K,
+                      float delta_v, float delta_d, int norm, int normalize_means,
+                      float w_var, float w_dist, float w_reg, float w_q,
+                      float* out_loss, float* out_terms, float* out_means,
+                      void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* grad_loss [1] f32 (device), grad_means [bs][K][C] or NULL, grad_emb [bs][C][H][W] out. */
+int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, const int* n_objects,
+                      int bs, int C, int H, int W, int K,
+                      float delta_v, float delta_d, int norm, int normalize_means,
+                      float w_var, float w_dist, float w_reg, float w_q,
+                      const float* means, const float* grad_loss, const float* grad_means,
+                      float* grad_emb, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* Dense one-hot masks (kind 1..3) -> u8 label map; *not_onehot_flag (device int) is set to 1
+ * when some pixel has several non-zeros or a weight other than 1.
+ * Replaces the int64 one-hot expansion of lib/dataset.py:354-376 on the device side. */
+int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int H, int W,
+                         unsigned char* labels, int* not_onehot_flag, isa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISA_B200_H_ */

@@ -1,0 +1,94 @@
+"""ctypes binding of libisa_sm100.so (the C-ABI declared in include/isa_b200.h).
+
+There is no fallback: if the library is missing or a call fails, the op raises.
+Mirrors the reference's lazily-loaded native module idiom
+(/root/reference/code/lib/archs/modules/sru/sru_functional.py:13-37).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisa_sm100.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_size_t = ctypes.c_size_t
+c_uint64 = ctypes.c_uint64
+c_double = ctypes.c_double
+
+# name -> (restype, argtypes); kept in the order of include/isa_b200.h
+SIGNATURES = {
+    "isa_last_error": (ctypes.c_char_p, []),
+    "isa_version": (c_int, []),
+    "isa_num_sms": (c_int, [ctypes.POINTER(c_int)]),
+    # discriminative loss
+    "isa_disc_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "isa_disc_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_int,
+                                  c_float, c_float, c_int, c_int,
+                                  c_float, c_float, c_float, c_float,
+                                  c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
+    "isa_disc_loss_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_int,
+                                  c_float, c_float, c_int, c_int,
+                                  c_float, c_float, c_float, c_float,
+                                  c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_onehot_to_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p]),
+}
+
+
+class IsaError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise IsaError(
+                "libisa_sm100.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python instance-segmentation-attention_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().isa_last_error()
+        raise IsaError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device (or host) address of a contiguous torch tensor, or NULL for None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensor handed to the C-ABI must be contiguous"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise IsaError("%s must be a CUDA tensor: the sm_100a kernels have no CPU fallback" % name)

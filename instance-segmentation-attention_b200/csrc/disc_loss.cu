@@ -1,0 +1,784 @@
+// Discriminative loss, forward and backward, as segmented reductions over the
+// embedding map.  Replaces the broadcast-and-reduce PyTorch graph of
+//   /root/reference/code/lib/losses/discriminative.py:7-62   (calculate_means)
+//   /root/reference/code/lib/losses/discriminative.py:65-95  (calculate_variance_term, else-branch)
+//   /root/reference/code/lib/losses/discriminative.py:98-132 (calculate_distance_term)
+//   /root/reference/code/lib/losses/discriminative.py:135-147 (calculate_regularization_term)
+//   /root/reference/code/lib/losses/discriminative.py:149-160 (calculate_q_regularization_term)
+//   /root/reference/code/lib/losses/discriminative.py:162-188 (discriminative_loss composite)
+//
+// Data layout in HBM: emb is the network's NCHW map [bs][C][H*W] (pixel index
+// contiguous), so a warp reads 32 consecutive pixels of one channel per load
+// (128 B, fully coalesced) and each thread keeps the C channel values of its
+// pixel in registers.  The target is read as handed over: a u8 label map
+// [bs][H*W] (255 = background) or the reference's dense one-hot/float mask
+// [bs][K][H*W] (f32 / i64 / u8).
+//
+// Forward = one cooperative kernel.  Each image is owned by G co-resident CTAs.
+//   phase 1: per-instance sums  s_k = sum_p m_pk x_p, counts, q-regulariser
+//   -- per-image barrier (all partial sums are in L2) --
+//   phase 2: means -> smem, hinge sum  sum_p m_pk max(|x_p-mu_k|-dv,0)^2 and the
+//            per-instance hinge-gradient sums A_k kept for backward; the second
+//            read of the image comes out of L2, not HBM.
+// A thread walks DOWN a pixel column: instance masks are spatially coherent, so
+// the running (label, partial sum) pair stays in registers until the label
+// changes and only then is flushed with fire-and-forget float REDs.
+//
+// Backward = a tiny per-image prep kernel (normalised-mean Jacobian, distance /
+// regulariser gradients on the K x C means) + one streaming pass that reads the
+// embedding and target once and writes grad_emb once.
+#include "isa_common.cuh"
+#include <math.h>
+
+namespace {
+
+enum { TGT_LABEL_U8 = 0, TGT_DENSE_F32 = 1, TGT_DENSE_I64 = 2, TGT_DENSE_U8 = 3 };
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct DiscWs {
+  // zeroed region
+  float* sums;        // [bs][K][C+1], last column = count
+  float* gsum;        // [bs][K][C]    A_k = sum_p m_pk * dh^2/dx
+  float* var_sum;     // [bs]
+  double* qsum;       // [1]
+  double* nfg;        // [1]
+  unsigned* img_cnt;  // [bs]
+  unsigned* done_cnt; // [1]
+  // not zeroed
+  float* rnorm;   // [bs][K]  |mu~_k| before normalisation
+  float* Nb;      // [bs]
+  float* dist_b;  // [bs]
+  float* reg_b;   // [bs]
+  float* T;       // [bs][K][C]  bwd: dL/d(mu~_k) / count_k
+  float* coef;    // [bs] cdir_b, then [1] cq
+  size_t zero_bytes;
+  size_t total_bytes;
+};
+
+static DiscWs carve(void* base, int bs, int C, int K) {
+  DiscWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += isa_align_up(bytes, 16);
+    return r;
+  };
+  w.qsum = (double*)take(sizeof(double));
+  w.nfg = (double*)take(sizeof(double));
+  w.sums = (float*)take(sizeof(float) * (size_t)bs * K * (C + 1));
+  w.gsum = (float*)take(sizeof(float) * (size_t)bs * K * C);
+  w.var_sum = (float*)take(sizeof(float) * bs);
+  w.img_cnt = (unsigned*)take(sizeof(unsigned) * bs);
+  w.done_cnt = (unsigned*)take(sizeof(unsigned));
+  w.zero_bytes = off;
+  w.rnorm = (float*)take(sizeof(float) * (size_t)bs * K);
+  w.Nb = (float*)take(sizeof(float) * bs);
+  w.dist_b = (float*)take(sizeof(float) * bs);
+  w.reg_b = (float*)take(sizeof(float) * bs);
+  w.T = (float*)take(sizeof(float) * (size_t)bs * K * C);
+  w.coef = (float*)take(sizeof(float) * (bs + 1));
+  w.total_bytes = off;
+  return w;
+}
+
+struct FwdParams {
+  const float* emb;
+  const void* target;
+  const int* n_objects;
+  int target_kind;
+  int bs, C, H, W, K;
+  float delta_v, delta_d;
+  int norm;
+  int normalize_means;
+  float w_var, w_dist, w_reg, w_q;
+  DiscWs ws;
+  float* out_loss;   // [1]
+  float* out_terms;  // [4] var, dist, reg, qreg (unweighted)
+  float* out_means;  // [bs][K][C]
+  int G;             // CTAs per image (1 => CTA loops over images, no inter-CTA barrier)
+  int strips, rowsplits, rpt;
+};
+
+// Reads the (up to K) mask weights of pixel p.  Returns the number of non-zero
+// entries; k1/w1 = the first one; fg = sum over all K channels
+// (discriminative.py:151 sums the target over every instance channel).
+template <int KIND>
+__device__ __forceinline__ int read_mask(const void* __restrict__ tgt, size_t img_off_px, int p, int P, int K,
+                                         int& k1, float& w1, float& fg) {
+  if (KIND == TGT_LABEL_U8) {
+    const unsigned char l = __ldg((const unsigned char*)tgt + img_off_px + p);
+    if ((int)l < K) { k1 = l; w1 = 1.f; fg = 1.f; return 1; }
+    k1 = -1; w1 = 0.f; fg = 0.f; return 0;
+  } else {
+    int nnz = 0; k1 = -1; w1 = 0.f; fg = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float m;
+      const size_t idx = (img_off_px * (size_t)K) + (size_t)k * P + p;
+      if (KIND == TGT_DENSE_F32) m = __ldg((const float*)tgt + idx);
+      else if (KIND == TGT_DENSE_I64) m = (float)__ldg((const long long*)tgt + idx);
+      else m = (float)__ldg((const unsigned char*)tgt + idx);
+      if (m != 0.f) { fg += m; if (nnz == 0) { k1 = k; w1 = m; } ++nnz; }
+    }
+    return nnz;
+  }
+}
+template <int KIND>
+__device__ __forceinline__ float read_mask_k(const void* __restrict__ tgt, size_t img_off_px, int p, int P, int K, int k) {
+  const size_t idx = (img_off_px * (size_t)K) + (size_t)k * P + p;
+  if (KIND == TGT_DENSE_F32) return __ldg((const float*)tgt + idx);
+  if (KIND == TGT_DENSE_I64) return (float)__ldg((const long long*)tgt + idx);
+  if (KIND == TGT_DENSE_U8) return (float)__ldg((const unsigned char*)tgt + idx);
+  return 0.f;
+}
+
+template <int CP>
+__device__ __forceinline__ void flush_run(float* __restrict__ dst_row, int stride_has_cnt, const float (&acc)[CP], float cnt, int C) {
+#pragma unroll
+  for (int c = 0; c < CP; ++c)
+    if (c < C) atomicAdd(dst_row + c, acc[c]);
+  if (stride_has_cnt) atomicAdd(dst_row + C, cnt);
+}
+
+// hinge on one (pixel, instance) pair: returns w*h^2 and the gradient scale so
+// that d(w h^2)/dx_c = gs * dir_c, dir_c = (x_c-mu_c) for L2, sign(x_c-mu_c) for L1.
+template <int CP>
+__device__ __forceinline__ float hinge_pair(const float (&x)[CP], const float* __restrict__ mu, int C, int norm, float delta_v, float w,
+                                            float (&dir)[CP], float& gs) {
+  float d = 0.f;
+  if (norm == 2) {
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) { dir[c] = x[c] - mu[c]; d = fmaf(dir[c], dir[c], d); }
+    d = sqrtf(d);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) { const float t = x[c] - mu[c]; d += fabsf(t); dir[c] = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f); }
+  }
+  const float h = fmaxf(d - delta_v, 0.f);
+  if (norm == 2) gs = (h > 0.f && d > 0.f) ? 2.f * w * h / d : 0.f;
+  else gs = (h > 0.f) ? 2.f * w * h : 0.f;
+  return w * h * h;
+}
+
+template <int CP, int KIND>
+__global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(const FwdParams prm) {
+  extern __shared__ float smem[];  // means [K][CP+1]
+  __shared__ float s_red[kWarps];
+  __shared__ int s_flag;
+  const int C = prm.C, K = prm.K, W = prm.W, H = prm.H, P = H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int MS = CP + 1;
+
+  const int G = prm.G;
+  const int b0 = blockIdx.x / G, g = blockIdx.x % G;
+  const int img_step = gridDim.x / G;
+  const int tiles = prm.strips * prm.rowsplits;
+  const int warps_per_img = G * kWarps;
+
+  double q_acc = 0.0, nfg_acc = 0.0;
+  int round = 0;
+  for (int b = b0; b < prm.bs; b += img_step, ++round) {
+    const int nb = min(max(__ldg(prm.n_objects + b), 0), K);
+    const float* __restrict__ emb = prm.emb + (size_t)b * C * P;
+    const size_t img_off_px = (size_t)b * P;
+    float* __restrict__ sums = prm.ws.sums + (size_t)b * K * (C + 1);
+
+    // ---------------- phase 1: per-instance sums, counts, q-regulariser ----------------
+    for (int t = g * kWarps + warp; t < tiles; t += warps_per_img) {
+      const int strip = t % prm.strips, rs = t / prm.strips;
+      const int xcol = strip * 32 + lane;
+      const int y0 = rs * prm.rpt, y1 = min(H, y0 + prm.rpt);
+      if (xcol >= W) continue;
+      float acc[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+      float cnt = 0.f;
+      float q_tile = 0.f, nfg_tile = 0.f;
+      int cur = -1;
+#pragma unroll 2
+      for (int y = y0; y < y1; ++y) {
+        const int p = y * W + xcol;
+        int k1; float w1, fg;
+        const int nnz = read_mask<KIND>(prm.target, img_off_px, p, P, K, k1, w1, fg);
+        float x[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
+        // q-regulariser: (|x*fg|_2 - 1)^2 for EVERY pixel (background adds 1).
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) { const float tq = x[c] * fg; ss = fmaf(tq, tq, ss); }
+        const float l2 = sqrtf(ss);
+        q_tile += (l2 - 1.f) * (l2 - 1.f);
+        nfg_tile += fg;
+        if (nnz == 1) {
+          if (k1 < nb) {
+            if (k1 != cur) {
+              if (cur >= 0) flush_run<CP>(sums + (size_t)cur * (C + 1), 1, acc, cnt, C);
+#pragma unroll
+              for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+              cnt = 0.f; cur = k1;
+            }
+#pragma unroll
+            for (int c = 0; c < CP; ++c) acc[c] = fmaf(w1, x[c], acc[c]);
+            cnt += w1;
+          }
+        } else if (nnz > 1) {
+          // soft / overlapping masks: every non-zero entry goes straight to L2.
+          for (int k = k1; k < nb; ++k) {
+            const float m = read_mask_k<KIND>(prm.target, img_off_px, p, P, K, k);
+            if (m != 0.f) {
+              float* row = sums + (size_t)k * (C + 1);
+#pragma unroll
+              for (int c = 0; c < CP; ++c) if (c < C) atomicAdd(row + c, m * x[c]);
+              atomicAdd(row + C, m);
+            }
+          }
+        }
+      }
+      if (cur >= 0) flush_run<CP>(sums + (size_t)cur * (C + 1), 1, acc, cnt, C);
+      q_acc += (double)q_tile;
+      nfg_acc += (double)nfg_tile;
+    }
+
+    // ---------------- per-image barrier ----------------
+    if (G > 1) {
+      group_barrier(prm.ws.img_cnt + b, (unsigned)G);
+    } else {
+      __threadfence();
+      __syncthreads();
+    }
+
+    // ---------------- means -> smem ----------------
+    for (int k = warp; k < K; k += kWarps) {
+      float v = 0.f;
+      float cntk = 0.f;
+      if (k < nb) {
+        cntk = __ldcg(sums + (size_t)k * (C + 1) + C);
+        if (lane < C) v = __ldcg(sums + (size_t)k * (C + 1) + lane) / cntk;
+        // CP may exceed 32 (CP=64): second half handled below
+      }
+      float v2 = 0.f;
+      if (CP > 32 && k < nb && lane + 32 < C) v2 = __ldcg(sums + (size_t)k * (C + 1) + lane + 32) / cntk;
+      float r = 1.f;
+      if (k < nb) {
+        const float n2 = warp_sum(v * v + v2 * v2);
+        r = sqrtf(n2);
+        if (prm.normalize_means) { v = v / r; v2 = v2 / r; }
+      }
+      if (lane < CP) smem[k * MS + lane] = v;
+      if (CP > 32 && lane + 32 < CP) smem[k * MS + lane + 32] = v2;
+      if (g == 0) {
+        if (lane < C) prm.out_means[((size_t)b * K + k) * C + lane] = v;
+        if (CP > 32 && lane + 32 < C) prm.out_means[((size_t)b * K + k) * C + lane + 32] = v2;
+        if (lane == 0) prm.ws.rnorm[(size_t)b * K + k] = r;
+      }
+    }
+    __syncthreads();
+
+    if (g == 0) {
+      // N_b, distance term and regulariser of this image (K^2*C work, one CTA).
+      float nsum = 0.f;
+      for (int k = threadIdx.x; k < nb; k += kThreads) {
+        const float ck = __ldcg(sums + (size_t)k * (C + 1) + C);
+        // an instance id below n_objects with no pixels makes the reference's
+        // mean 0/0 and its whole loss NaN (discriminative.py:41-42,84-85)
+        nsum += (ck == 0.f) ? nanf("") : ck;
+      }
+      float dsum = 0.f, rsum = 0.f;
+      if (prm.w_dist != 0.f && nb > 1) {
+        for (int ij = threadIdx.x; ij < nb * nb; ij += kThreads) {
+          const int i = ij / nb, j = ij % nb;
+          if (i == j) continue;
+          float e = 0.f;
+          for (int c = 0; c < C; ++c) {
+            const float t = smem[i * MS + c] - smem[j * MS + c];
+            e = (prm.norm == 2) ? fmaf(t, t, e) : e + fabsf(t);
+          }
+          if (prm.norm == 2) e = sqrtf(e);
+          const float m = fmaxf(2.f * prm.delta_d - e, 0.f);
+          dsum = fmaf(m, m, dsum);
+        }
+      }
+      if (prm.w_reg != 0.f) {
+        for (int k = threadIdx.x; k < nb; k += kThreads) {
+          float e = 0.f;
+          for (int c = 0; c < C; ++c) {
+            const float t = smem[k * MS + c];
+            e = (prm.norm == 2) ? fmaf(t, t, e) : e + fabsf(t);
+          }
+          rsum += (prm.norm == 2) ? sqrtf(e) : e;
+        }
+      }
+      nsum = warp_sum(nsum); dsum = warp_sum(dsum); rsum = warp_sum(rsum);
+      __shared__ float s3[3][kWarps];
+      if (lane == 0) { s3[0][warp] = nsum; s3[1][warp] = dsum; s3[2][warp] = rsum; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float a = 0.f, d = 0.f, r = 0.f;
+        for (int w = 0; w < kWarps; ++w) { a += s3[0][w]; d += s3[1][w]; r += s3[2][w]; }
+        prm.ws.Nb[b] = a;
+        prm.ws.dist_b[b] = (nb > 1) ? d / (float)(nb * (nb - 1)) : 0.f;
+        prm.ws.reg_b[b] = r / (float)nb;  // torch.mean over an empty slice is nan, as 0/0 here
+      }
+    }
+
+    // ---------------- phase 2: hinge sum + per-instance hinge-gradient sums ----------------
+    float var_acc = 0.f;
+    float* __restrict__ gsum = prm.ws.gsum + (size_t)b * K * C;
+    for (int t = g * kWarps + warp; t < tiles; t += warps_per_img) {
+      const int strip = t % prm.strips, rs = t / prm.strips;
+      const int xcol = strip * 32 + lane;
+      const int y0 = rs * prm.rpt, y1 = min(H, y0 + prm.rpt);
+      if (xcol >= W) continue;
+      float acc[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+      int cur = -1;
+#pragma unroll 2
+      for (int y = y0; y < y1; ++y) {
+        const int p = y * W + xcol;
+        int k1; float w1, fg;
+        const int nnz = read_mask<KIND>(prm.target, img_off_px, p, P, K, k1, w1, fg);
+        if (nnz == 0 || k1 >= nb) continue;
+        float x[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
+        float dir[CP]; float gs;
+        if (nnz == 1) {
+          var_acc += hinge_pair<CP>(x, smem + k1 * MS, C, prm.norm, prm.delta_v, w1, dir, gs);
+          if (k1 != cur) {
+            if (cur >= 0) flush_run<CP>(gsum + (size_t)cur * C, 0, acc, 0.f, C);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+            cur = k1;
+          }
+#pragma unroll
+          for (int c = 0; c < CP; ++c) if (c < C) acc[c] = fmaf(gs, dir[c], acc[c]);
+        } else {
+          for (int k = k1; k < nb; ++k) {
+            const float m = read_mask_k<KIND>(prm.target, img_off_px, p, P, K, k);
+            if (m != 0.f) {
+              var_acc += hinge_pair<CP>(x, smem + k * MS, C, prm.norm, prm.delta_v, m, dir, gs);
+#pragma unroll
+              for (int c = 0; c < CP; ++c) if (c < C) atomicAdd(gsum + (size_t)k * C + c, gs * dir[c]);
+            }
+          }
+        }
+      }
+      if (cur >= 0) flush_run<CP>(gsum + (size_t)cur * C, 0, acc, 0.f, C);
+    }
+    var_acc = warp_sum(var_acc);
+    if (lane == 0) s_red[warp] = var_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = 0.f;
+      for (int w = 0; w < kWarps; ++w) v += s_red[w];
+      atomicAdd(prm.ws.var_sum + b, v);
+    }
+    __syncthreads();  // smem means are reused by the next image
+  }
+
+  // ---------------- q-regulariser partials ----------------
+  q_acc = warp_sum_d(q_acc);
+  nfg_acc = warp_sum_d(nfg_acc);
+  if (lane == 0) { atomicAdd(prm.ws.qsum, q_acc); atomicAdd(prm.ws.nfg, nfg_acc); }
+
+  // ---------------- last CTA: combine the scalars ----------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = (atomicAdd(prm.ws.done_cnt, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_flag && warp == 0) {
+    __threadfence();
+    float v = 0.f, d = 0.f, r = 0.f;
+    for (int b = lane; b < prm.bs; b += 32) {
+      v += __ldcg(prm.ws.var_sum + b) / __ldcg(prm.ws.Nb + b);
+      d += __ldcg(prm.ws.dist_b + b);
+      r += __ldcg(prm.ws.reg_b + b);
+    }
+    v = warp_sum(v); d = warp_sum(d); r = warp_sum(r);
+    if (lane == 0) {
+      const float inv_bs = 1.f / (float)prm.bs;
+      const double qs = __ldcg(prm.ws.qsum), nf = __ldcg(prm.ws.nfg);
+      // discriminative.py:153-159: num = int(sum(target)); loss = sum(...)/num
+      const float qreg = (float)(qs / (double)(long long)nf);
+      const float var_t = v * inv_bs;
+      const float dist_t = (prm.w_dist != 0.f) ? d * inv_bs : 0.f;
+      const float reg_t = (prm.w_reg != 0.f) ? r * inv_bs : 0.f;
+      prm.out_terms[0] = var_t; prm.out_terms[1] = dist_t; prm.out_terms[2] = reg_t; prm.out_terms[3] = qreg;
+      float loss = 0.f;
+      if (prm.w_var != 0.f) loss += prm.w_var * var_t;
+      if (prm.w_dist != 0.f) loss += prm.w_dist * dist_t;
+      if (prm.w_reg != 0.f) loss += prm.w_reg * reg_t;
+      if (prm.w_q != 0.f) loss += prm.w_q * qreg;
+      prm.out_loss[0] = loss;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward
+struct BwdParams {
+  const float* emb;
+  const void* target;
+  const int* n_objects;
+  int target_kind;
+  int bs, C, H, W, K;
+  float delta_v, delta_d;
+  int norm;
+  int normalize_means;
+  float w_var, w_dist, w_reg, w_q;
+  DiscWs ws;
+  const float* means;       // [bs][K][C] forward output
+  const float* grad_loss;   // [1] device scalar
+  const float* grad_means;  // [bs][K][C] or null
+  float* grad_emb;          // [bs][C][P]
+};
+
+// One CTA per image: T_k = dL/d(mu~_k) / count_k  for k < n_b.
+__global__ void __launch_bounds__(128) disc_bwd_prep_kernel(const BwdParams prm) {
+  extern __shared__ float sm[];  // Gam [K][C]
+  const int b = blockIdx.x, C = prm.C, K = prm.K;
+  const int nb = min(max(__ldg(prm.n_objects + b), 0), K);
+  const float go = __ldg(prm.grad_loss);
+  const float inv_bs = 1.f / (float)prm.bs;
+  const float Nb = prm.ws.Nb[b];
+  const float cdir = go * prm.w_var * inv_bs / Nb;
+  const float* mu = prm.means + (size_t)b * K * C;
+  const float* gsum = prm.ws.gsum + (size_t)b * K * C;
+  // Gamma_k = dL/dmu_k
+  for (int i = threadIdx.x; i < nb * C; i += blockDim.x) {
+    const int k = i / C, c = i % C;
+    float gam = -cdir * gsum[i];
+    if (prm.grad_means) gam += prm.grad_means[((size_t)b * K + k) * C + c];
+    if (prm.w_reg != 0.f) {
+      const float cr = go * prm.w_reg * inv_bs / (float)nb;
+      if (prm.norm == 2) {
+        float e = 0.f;
+        for (int cc = 0; cc < C; ++cc) e = fmaf(mu[k * C + cc], mu[k * C + cc], e);
+        e = sqrtf(e);
+        if (e > 0.f) gam += cr * mu[k * C + c] / e;
+      } else {
+        const float t = mu[k * C + c];
+        gam += cr * ((t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f));
+      }
+    }
+    if (prm.w_dist != 0.f && nb > 1) {
+      const float cd = go * prm.w_dist * inv_bs / (float)(nb * (nb - 1));
+      float acc = 0.f;
+      for (int j = 0; j < nb; ++j) {
+        if (j == k) continue;
+        float e = 0.f;
+        for (int cc = 0; cc < C; ++cc) {
+          const float t = mu[k * C + cc] - mu[j * C + cc];
+          e = (prm.norm == 2) ? fmaf(t, t, e) : e + fabsf(t);
+        }
+        if (prm.norm == 2) e = sqrtf(e);
+        const float m = fmaxf(2.f * prm.delta_d - e, 0.f);
+        if (m > 0.f) {
+          const float t = mu[k * C + c] - mu[j * C + c];
+          if (prm.norm == 2) { if (e > 0.f) acc -= 4.f * m * t / e; }
+          else acc -= 4.f * m * ((t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f));
+        }
+      }
+      gam += cd * acc;
+    }
+    sm[i] = gam;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    const int k = i / C, c = i % C;
+    float t = 0.f;
+    if (k < nb) {
+      const float cntk = prm.ws.sums[((size_t)b * K + k) * (C + 1) + C];
+      float gam = sm[i];
+      if (prm.normalize_means) {
+        float dot = 0.f;
+        for (int cc = 0; cc < C; ++cc) dot = fmaf(mu[k * C + cc], sm[k * C + cc], dot);
+        gam = (gam - mu[k * C + c] * dot) / prm.ws.rnorm[(size_t)b * K + k];
+      }
+      t = gam / cntk;
+    }
+    prm.ws.T[(size_t)b * K * C + i] = t;
+  }
+  if (threadIdx.x == 0) {
+    prm.ws.coef[b] = cdir;
+    if (b == 0) {
+      const double nf = *prm.ws.nfg;
+      prm.ws.coef[prm.bs] = (float)((double)(go * prm.w_q) / (double)(long long)nf);
+    }
+  }
+}
+
+template <int CP, int KIND>
+__global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm) {
+  extern __shared__ float sm[];  // mu [K][CP+1], T [K][CP+1]
+  const int C = prm.C, K = prm.K, P = prm.H * prm.W;
+  const int MS = CP + 1;
+  const int b = blockIdx.y;
+  const int nb = min(max(__ldg(prm.n_objects + b), 0), K);
+  float* s_mu = sm;
+  float* s_T = sm + K * MS;
+  for (int i = threadIdx.x; i < K * C; i += kThreads) {
+    const int k = i / C, c = i % C;
+    s_mu[k * MS + c] = prm.means[(size_t)b * K * C + i];
+    s_T[k * MS + c] = prm.ws.T[(size_t)b * K * C + i];
+  }
+  __syncthreads();
+  const float cdir = prm.ws.coef[b];
+  const float cq = prm.ws.coef[prm.bs];
+  const float* __restrict__ emb = prm.emb + (size_t)b * C * P;
+  float* __restrict__ gout = prm.grad_emb + (size_t)b * C * P;
+  const size_t img_off_px = (size_t)b * P;
+  for (int p = blockIdx.x * kThreads + threadIdx.x; p < P; p += gridDim.x * kThreads) {
+    int k1; float w1, fg;
+    const int nnz = read_mask<KIND>(prm.target, img_off_px, p, P, K, k1, w1, fg);
+    float x[CP], gr[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
+    // q-regulariser: d/dx (|x fg| - 1)^2 = 2 (l-1) fg^2 x / l
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) { const float tq = x[c] * fg; ss = fmaf(tq, tq, ss); }
+    const float l2 = sqrtf(ss);
+    const float qs = (l2 > 0.f) ? cq * 2.f * (l2 - 1.f) * fg * fg / l2 : 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) gr[c] = qs * x[c];
+    if (nnz == 1) {
+      if (k1 < nb) {
+        float dir[CP]; float gs;
+        hinge_pair<CP>(x, s_mu + k1 * MS, C, prm.norm, prm.delta_v, w1, dir, gs);
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+          if (c < C) gr[c] += cdir * gs * dir[c] + w1 * s_T[k1 * MS + c];
+      }
+    } else if (nnz > 1) {
+      for (int k = k1; k < nb; ++k) {
+        const float m = read_mask_k<KIND>(prm.target, img_off_px, p, P, K, k);
+        if (m != 0.f) {
+          float dir[CP]; float gs;
+          hinge_pair<CP>(x, s_mu + k * MS, C, prm.norm, prm.delta_v, m, dir, gs);
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+            if (c < C) gr[c] += cdir * gs * dir[c] + m * s_T[k * MS + c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) gout[(size_t)c * P + p] = gr[c];
+  }
+}
+
+// Dense one-hot mask -> u8 label map (255 = background); *flag |= 1 if some
+// pixel is not one-hot (several non-zeros, or a value other than 1).
+template <int KIND>
+__global__ void onehot_to_labels_kernel(const void* __restrict__ tgt, unsigned char* __restrict__ labels, int bs, int K, int P, int* flag) {
+  const size_t total = (size_t)bs * P;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / P), p = (int)(i % P);
+    int k1; float w1, fg;
+    const int nnz = read_mask<KIND>(tgt, (size_t)b * P, p, P, K, k1, w1, fg);
+    labels[i] = (nnz >= 1) ? (unsigned char)k1 : (unsigned char)255;
+    if (nnz > 1 || (nnz == 1 && w1 != 1.f)) atomicOr(flag, 1);
+  }
+}
+
+int allow_smem(const void* fn, size_t smem) {
+  if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return ISA_OK;
+}
+
+template <int CP>
+int launch_fwd(const FwdParams& prm, int grid, size_t smem, cudaStream_t stream) {
+  void* args[] = {(void*)&prm};
+  const void* fn = nullptr;
+  switch (prm.target_kind) {
+    case TGT_LABEL_U8: fn = (const void*)disc_fwd_kernel<CP, TGT_LABEL_U8>; break;
+    case TGT_DENSE_F32: fn = (const void*)disc_fwd_kernel<CP, TGT_DENSE_F32>; break;
+    case TGT_DENSE_I64: fn = (const void*)disc_fwd_kernel<CP, TGT_DENSE_I64>; break;
+    default: fn = (const void*)disc_fwd_kernel<CP, TGT_DENSE_U8>; break;
+  }
+  ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
+  return ISA_OK;
+}
+template <int CP>
+int occupancy_fwd(int kind, size_t smem, int* out) {
+  const void* fn = nullptr;
+  switch (kind) {
+    case TGT_LABEL_U8: fn = (const void*)disc_fwd_kernel<CP, TGT_LABEL_U8>; break;
+    case TGT_DENSE_F32: fn = (const void*)disc_fwd_kernel<CP, TGT_DENSE_F32>; break;
+    case TGT_DENSE_I64: fn = (const void*)disc_fwd_kernel<CP, TGT_DENSE_I64>; break;
+    default: fn = (const void*)disc_fwd_kernel<CP, TGT_DENSE_U8>; break;
+  }
+  int rc = allow_smem(fn, smem);
+  if (rc) return rc;
+  ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fn, kThreads, smem));
+  return ISA_OK;
+}
+template <int CP>
+int launch_bwd(const BwdParams& prm, dim3 grid, size_t smem, cudaStream_t stream) {
+  if (smem > 48 * 1024) {
+    int rc = 0;
+    switch (prm.target_kind) {
+      case TGT_LABEL_U8: rc = allow_smem((const void*)disc_bwd_kernel<CP, TGT_LABEL_U8>, smem); break;
+      case TGT_DENSE_F32: rc = allow_smem((const void*)disc_bwd_kernel<CP, TGT_DENSE_F32>, smem); break;
+      case TGT_DENSE_I64: rc = allow_smem((const void*)disc_bwd_kernel<CP, TGT_DENSE_I64>, smem); break;
+      default: rc = allow_smem((const void*)disc_bwd_kernel<CP, TGT_DENSE_U8>, smem); break;
+    }
+    if (rc) return rc;
+  }
+  switch (prm.target_kind) {
+    case TGT_LABEL_U8: disc_bwd_kernel<CP, TGT_LABEL_U8><<<grid, kThreads, smem, stream>>>(prm); break;
+    case TGT_DENSE_F32: disc_bwd_kernel<CP, TGT_DENSE_F32><<<grid, kThreads, smem, stream>>>(prm); break;
+    case TGT_DENSE_I64: disc_bwd_kernel<CP, TGT_DENSE_I64><<<grid, kThreads, smem, stream>>>(prm); break;
+    default: disc_bwd_kernel<CP, TGT_DENSE_U8><<<grid, kThreads, smem, stream>>>(prm); break;
+  }
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+int pick_cp(int C) { return C <= 8 ? 8 : C <= 16 ? 16 : C <= 24 ? 24 : C <= 32 ? 32 : 64; }
+
+int check_common(int target_kind, int bs, int C, int H, int W, int K, int norm) {
+  ISA_CHECK_ARG(target_kind >= 0 && target_kind <= 3, "disc_loss: target_kind %d not in 0..3", target_kind);
+  ISA_CHECK_ARG(bs > 0 && C > 0 && H > 0 && W > 0 && K > 0, "disc_loss: non-positive dimension (bs=%d C=%d H=%d W=%d K=%d)", bs, C, H, W, K);
+  ISA_CHECK_ARG(C <= 64, "disc_loss: embedding width C=%d > 64 is not supported", C);
+  ISA_CHECK_ARG(K <= 254, "disc_loss: K=%d > 254 instances (u8 label map limit)", K);
+  ISA_CHECK_ARG((long long)H * W < (1ll << 30), "disc_loss: H*W too large");
+  ISA_CHECK_ARG(norm == 1 || norm == 2, "disc_loss: norm must be 1 or 2 (got %d)", norm);
+  return ISA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t isa_disc_loss_workspace_bytes(int bs, int C, int K) {
+  if (bs <= 0 || C <= 0 || K <= 0) return 0;
+  return carve(nullptr, bs, C, K).total_bytes;
+}
+
+int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, const int* n_objects,
+                      int bs, int C, int H, int W, int K,
+                      float delta_v, float delta_d, int norm, int normalize_means,
+                      float w_var, float w_dist, float w_reg, float w_q,
+                      float* out_loss, float* out_terms, float* out_means,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  int rc = check_common(target_kind, bs, C, H, W, K, norm);
+  if (rc) return rc;
+  ISA_CHECK_ARG(emb && target && n_objects && out_loss && out_terms && out_means && workspace, "disc_loss_fwd: null pointer");
+  FwdParams prm;
+  prm.ws = carve(workspace, bs, C, K);
+  if (workspace_bytes < prm.ws.total_bytes) {
+    isa_set_error("disc_loss_fwd: workspace %zu < required %zu bytes", workspace_bytes, prm.ws.total_bytes);
+    return ISA_ERR_WORKSPACE;
+  }
+  IsaDeviceInfo di;
+  rc = isa_device_info(&di);
+  if (rc) return rc;
+  prm.emb = emb; prm.target = target; prm.n_objects = n_objects; prm.target_kind = target_kind;
+  prm.bs = bs; prm.C = C; prm.H = H; prm.W = W; prm.K = K;
+  prm.delta_v = delta_v; prm.delta_d = delta_d; prm.norm = norm; prm.normalize_means = normalize_means;
+  prm.w_var = w_var; prm.w_dist = w_dist; prm.w_reg = w_reg; prm.w_q = w_q;
+  prm.out_loss = out_loss; prm.out_terms = out_terms; prm.out_means = out_means;
+
+  const int CP = pick_cp(C);
+  const size_t smem = sizeof(float) * (size_t)K * (CP + 1);
+  int occ = 0;
+  switch (CP) {
+    case 8: rc = occupancy_fwd<8>(target_kind, smem, &occ); break;
+    case 16: rc = occupancy_fwd<16>(target_kind, smem, &occ); break;
+    case 24: rc = occupancy_fwd<24>(target_kind, smem, &occ); break;
+    case 32: rc = occupancy_fwd<32>(target_kind, smem, &occ); break;
+    default: rc = occupancy_fwd<64>(target_kind, smem, &occ); break;
+  }
+  if (rc) return rc;
+  ISA_CHECK_ARG(occ >= 1, "disc_loss_fwd: kernel does not fit on an SM (smem %zu)", smem);
+  const int NB = di.num_sms * occ;  // co-resident CTAs
+  int G, grid;
+  if (bs <= NB) { G = NB / bs; grid = G * bs; } else { G = 1; grid = NB; }
+  prm.G = G;
+  prm.strips = (W + 31) / 32;
+  int rowsplits = (G * kWarps) / prm.strips;
+  rowsplits = rowsplits < 1 ? 1 : (rowsplits > H ? H : rowsplits);
+  prm.rpt = (H + rowsplits - 1) / rowsplits;
+  prm.rowsplits = (H + prm.rpt - 1) / prm.rpt;
+
+  ISA_CUDA(cudaMemsetAsync(workspace, 0, prm.ws.zero_bytes, stream));
+  switch (CP) {
+    case 8: return launch_fwd<8>(prm, grid, smem, stream);
+    case 16: return launch_fwd<16>(prm, grid, smem, stream);
+    case 24: return launch_fwd<24>(prm, grid, smem, stream);
+    case 32: return launch_fwd<32>(prm, grid, smem, stream);
+    default: return launch_fwd<64>(prm, grid, smem, stream);
+  }
+}
+
+int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, const int* n_objects,
+                      int bs, int C, int H, int W, int K,
+                      float delta_v, float delta_d, int norm, int normalize_means,
+                      float w_var, float w_dist, float w_reg, float w_q,
+                      const float* means, const float* grad_loss, const float* grad_means,
+                      float* grad_emb, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  int rc = check_common(target_kind, bs, C, H, W, K, norm);
+  if (rc) return rc;
+  ISA_CHECK_ARG(emb && target && n_objects && means && grad_loss && grad_emb && workspace, "disc_loss_bwd: null pointer");
+  BwdParams prm;
+  prm.ws = carve(workspace, bs, C, K);
+  if (workspace_bytes < prm.ws.total_bytes) {
+    isa_set_error("disc_loss_bwd: workspace %zu < required %zu bytes", workspace_bytes, prm.ws.total_bytes);
+    return ISA_ERR_WORKSPACE;
+  }
+  IsaDeviceInfo di;
+  rc = isa_device_info(&di);
+  if (rc) return rc;
+  prm.emb = emb; prm.target = target; prm.n_objects = n_objects; prm.target_kind = target_kind;
+  prm.bs = bs; prm.C = C; prm.H = H; prm.W = W; prm.K = K;
+  prm.delta_v = delta_v; prm.delta_d = delta_d; prm.norm = norm; prm.normalize_means = normalize_means;
+  prm.w_var = w_var; prm.w_dist = w_dist; prm.w_reg = w_reg; prm.w_q = w_q;
+  prm.means = means; prm.grad_loss = grad_loss; prm.grad_means = grad_means; prm.grad_emb = grad_emb;
+
+  disc_bwd_prep_kernel<<<bs, 128, sizeof(float) * (size_t)K * C, stream>>>(prm);
+  ISA_CUDA(cudaGetLastError());
+
+  const int CP = pick_cp(C);
+  const size_t smem = sizeof(float) * 2 * (size_t)K * (CP + 1);
+  const int P = H * W;
+  int gx = (P + kThreads - 1) / kThreads;
+  const int target_ctas = di.num_sms * 8;
+  int per_img = (target_ctas + bs - 1) / bs;
+  if (gx > per_img) gx = per_img;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, bs);
+  ISA_CHECK_ARG(bs <= 65535, "disc_loss_bwd: bs=%d > 65535", bs);
+  switch (CP) {
+    case 8: return launch_bwd<8>(prm, grid, smem, stream);
+    case 16: return launch_bwd<16>(prm, grid, smem, stream);
+    case 24: return launch_bwd<24>(prm, grid, smem, stream);
+    case 32: return launch_bwd<32>(prm, grid, smem, stream);
+    default: return launch_bwd<64>(prm, grid, smem, stream);
+  }
+}
+
+int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int H, int W,
+                         unsigned char* labels, int* not_onehot_flag, cudaStream_t stream) {
+  ISA_CHECK_ARG(target_kind >= 1 && target_kind <= 3, "onehot_to_labels: target_kind %d is not a dense kind (1..3)", target_kind);
+  ISA_CHECK_ARG(target && labels && not_onehot_flag, "onehot_to_labels: null pointer");
+  ISA_CHECK_ARG(bs > 0 && K > 0 && K <= 254 && H > 0 && W > 0, "onehot_to_labels: bad dimensions");
+  const int P = H * W;
+  const size_t total = (size_t)bs * P;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  ISA_CUDA(cudaMemsetAsync(not_onehot_flag, 0, sizeof(int), stream));
+  if (target_kind == TGT_DENSE_F32) onehot_to_labels_kernel<TGT_DENSE_F32><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, not_onehot_flag);
+  else if (target_kind == TGT_DENSE_I64) onehot_to_labels_kernel<TGT_DENSE_I64><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, not_onehot_flag);
+  else onehot_to_labels_kernel<TGT_DENSE_U8><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, not_onehot_flag);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+}  // extern "C"
