@@ -77,6 +77,46 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
 int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int H, int W,
                          unsigned char* labels, int* not_onehot_flag, isa_stream_t stream);
 
+/* ------------------------------------------------------------------ embedding clustering
+ * Replaces sklearn.cluster.KMeans(n_clusters=k, n_init=35, max_iter=500).fit_predict(X) as called by
+ *   /root/reference/code/lib/prediction.py:72-74
+ * (scikit-learn is third party, not under /root/reference; algorithm restated from scikit-learn 1.9.0:
+ * sklearn/cluster/_kmeans.py:180-283 k-means++, :625-760 Lloyd loop, :1463-1563 fit,
+ * _k_means_lloyd.pyx:26-211, _k_means_common.pyx:13-262; arithmetic contract: oracle/kmeans_oracle.c).
+ * X           [C][ld] f32, FEATURE-major; the first n columns are the points (not modified)
+ * n_ptr       device int: number of points (so the fg count never visits the host)
+ * uniforms    device f64 [n_init][1 + (k-1)*n_local_trials]: the numpy RandomState(seed).random_sample
+ *             stream KMeans consumes (choice for the first centre, uniform for the D^2 draws); or NULL with
+ * init_centers device f32 [n_init][k][C] (array init; the data mean is subtracted like KMeans.fit does)
+ * labels_out  [ld] i32 (first n valid), centers_out [k][C], inertia_out [n_init] f64, n_iter_out [n_init],
+ * seed_idx_out [n_init][k] (k-means++ picks, may be NULL),
+ * info        [4] i32: status (0 ok, 1 n<k, 2 non-finite input), best restart, n, Lloyd iterations run.
+ */
+size_t isa_kmeans_workspace_bytes(int ld, int C, int k, int n_init);
+
+int isa_kmeans_fit(const float* X, const int* n_ptr, int ld, int C, int k, int n_init, int max_iter, double tol_rel,
+                   int n_local_trials, const double* uniforms, const float* init_centers,
+                   int* labels_out, float* centers_out, double* inertia_out, int* n_iter_out, int* seed_idx_out,
+                   int* info, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* Foreground compaction: cls = argmax over classes (first max), fg = cls != 0, points in np.where order.
+ *   /root/reference/code/lib/prediction.py:57-69
+ * sem [ncls][HW] f32, emb [C][HW] f32 -> cls_map [HW] u8, Xt [C][ld] f32, fg_index [HW] i32, n_out [1]. */
+size_t isa_fg_compact_workspace_bytes(int HW);
+
+int isa_fg_compact(const float* sem, const float* emb, int ncls, int C, int HW, int ld,
+                   unsigned char* cls_map, float* Xt, int* fg_index, int* n_out,
+                   void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* mask[fg_index[i]] = labels[i] + 1 (uint8, 0 = background), then cv2.resize(INTER_NEAREST) of the
+ * instance mask and the class map to (out_h, out_w).
+ *   /root/reference/code/lib/prediction.py:76-83 (scatter), :47-50 and :105-108 (up-sampling)
+ * ins_up / cls_up may be NULL. */
+int isa_scatter_labels_upsample(const int* labels, const int* fg_index, const int* n_ptr,
+                                const unsigned char* cls_map, int h, int w, int out_h, int out_w,
+                                unsigned char* ins_small, unsigned char* ins_up, unsigned char* cls_up,
+                                isa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

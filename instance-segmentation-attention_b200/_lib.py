@@ -42,6 +42,18 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_onehot_to_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
+    # clustering
+    "isa_kmeans_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "isa_kmeans_fit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_double,
+                               c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
+    "isa_fg_compact_workspace_bytes": (c_size_t, [c_int]),
+    "isa_fg_compact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
+    "isa_scatter_labels_upsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -79,6 +79,7 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
   if (threadIdx.x == 0) {
     atomicAdd(counter, 1u);
     while (ld_acquire_u32(counter) < target) { __nanosleep(32); }
+    __threadfence();  // acquire side: drop stale L1 lines before the CTA reads other CTAs' data
   }
   __syncthreads();
 }

@@ -1,0 +1,843 @@
+// GPU embedding clustering: k-means++ seeding + batched-restart Lloyd + best-restart
+// selection, all on the device with no host round trip.  Replaces
+//   sklearn.cluster.KMeans(n_clusters=k, n_init=35, max_iter=500).fit_predict(X)
+// as called by /root/reference/code/lib/prediction.py:72-74, using the same seeds stream
+// (numpy RandomState draws are made on the host and handed over as `uniforms`) and the same
+// iteration rule (E-step argmin |c|^2-2x.c with first-index ties, mean M-step, empty-cluster
+// relocation, strict-then-tol stop, E-step re-run, best inertia unless same clustering).
+//
+// Arithmetic contract (bit-exact with oracle/kmeans_oracle.c, which documents the mapping to
+// scikit-learn's sources):
+//   * per-pair arithmetic in fp32, explicit round-to-nearest intrinsics, fixed fmaf order;
+//   * every sum over points in exact 64-bit fixed point -> order independent, so atomics and
+//     incremental M-step updates ("move the points whose label changed") are exact.
+//
+// Layout: X is feature-major [C][ld] (what the fg compaction of the NCHW embedding produces),
+// so a warp reads 32 consecutive points of one feature per load; every restart keeps its
+// labels as u8 [n_init][ld]; per-restart centre sums are int64 [n_init][k][C].
+//
+// Kernels:  km_prep_max / km_prep_sums / km_prep_center   (one pass each over X)
+//           km_seed   one CTA per restart, greedy k-means++ (exact int64 prefix search)
+//           km_lloyd  ONE persistent cooperative kernel for all restarts and all iterations:
+//                     E-step tiles of every active restart -> grid barrier -> per-restart
+//                     update CTA -> grid barrier; then E-step re-run, inertia, selection.
+#include "isa_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int kLloydThreads = 256;
+constexpr int kPPT = 4;                         // points per thread in the E-step
+constexpr int kTile = kLloydThreads * kPPT;     // points per work item
+constexpr int kSeedThreads = 512;
+constexpr int kMaxL = 8;
+constexpr int kMaxK = 254;
+constexpr int kMaxInit = 64;
+
+struct KmScales {
+  int S_mean, S_x, S_d, S_t;
+  double p_mean, p_x, p_d, p_t;       // 2^S
+  double ip_mean, ip_x, ip_d, ip_t;   // 2^-S
+};
+
+struct KmWs {
+  // header (zeroed)
+  unsigned* maxabs_bits;   // [1]
+  int* status;             // [1] 0 ok, 1 n<k, 2 non-finite
+  unsigned* barrier;       // [1]
+  long long* colsum;       // [C]
+  long long* tolsum;       // [1]
+  long long* sums;         // [R][k][C]
+  int* cnt;                // [R][k]
+  long long* inertia_q;    // [R]
+  int* changed;            // [R]
+  int* state;              // [R] 0 active, 1 strict, 2 tol/max_iter
+  int* n_iter;             // [R]
+  size_t zero_bytes;
+  // not zeroed
+  float* mean;             // [C]
+  float* Xc;               // [C][ld]
+  float* closest;          // [R][ld]
+  float* centers;          // [R][k][C]
+  unsigned char* labels;   // [R][ld]
+  unsigned char* acct;     // [R][ld]
+  int* seed_idx;           // [R][k]
+  size_t total_bytes;
+};
+
+KmWs km_carve(void* base, int ld, int C, int k, int R) {
+  KmWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += isa_align_up(bytes, 256);
+    return r;
+  };
+  w.maxabs_bits = (unsigned*)take(4);
+  w.status = (int*)take(4);
+  w.barrier = (unsigned*)take(4);
+  w.colsum = (long long*)take(8 * (size_t)C);
+  w.tolsum = (long long*)take(8);
+  w.sums = (long long*)take(8 * (size_t)R * k * C);
+  w.cnt = (int*)take(4 * (size_t)R * k);
+  w.inertia_q = (long long*)take(8 * (size_t)R);
+  w.changed = (int*)take(4 * (size_t)R);
+  w.state = (int*)take(4 * (size_t)R);
+  w.n_iter = (int*)take(4 * (size_t)R);
+  w.zero_bytes = off;
+  w.mean = (float*)take(4 * (size_t)C);
+  w.Xc = (float*)take(4 * (size_t)C * ld);
+  w.closest = (float*)take(4 * (size_t)R * ld);
+  w.centers = (float*)take(4 * (size_t)R * k * C);
+  w.labels = (unsigned char*)take((size_t)R * ld);
+  w.acct = (unsigned char*)take((size_t)R * ld);
+  w.seed_idx = (int*)take(4 * (size_t)R * k);
+  w.total_bytes = off;
+  return w;
+}
+
+__host__ __device__ inline int ceil_log2_int(int v) {
+  int b = 0;
+  while ((1 << b) < v) ++b;
+  return b;
+}
+
+// Same rule as isa_km_oracle_scales (oracle/kmeans_oracle.c).
+__device__ inline KmScales km_scales(unsigned maxabs_bits, int n, int C) {
+  const float maxabs = __uint_as_float(maxabs_bits);
+  const int e_m = (maxabs > 0.f) ? (ilogbf(maxabs) + 1) : 0;
+  int bits = 0;
+  while (bits < 31 && (n >> bits) != 0) ++bits;
+  const int e_c = e_m + 1;
+  KmScales s;
+  s.S_mean = 62 - e_m - bits;
+  s.S_x = 62 - e_c - bits;
+  s.S_d = 62 - (2 * e_c + 2 + ceil_log2_int(C)) - bits;
+  s.S_t = 62 - 2 * e_c - bits - ceil_log2_int(C);
+  s.p_mean = ldexp(1.0, s.S_mean); s.ip_mean = ldexp(1.0, -s.S_mean);
+  s.p_x = ldexp(1.0, s.S_x);       s.ip_x = ldexp(1.0, -s.S_x);
+  s.p_d = ldexp(1.0, s.S_d);       s.ip_d = ldexp(1.0, -s.S_d);
+  s.p_t = ldexp(1.0, s.S_t);       s.ip_t = ldexp(1.0, -s.S_t);
+  return s;
+}
+
+// llrint(ldexp((double)v, S)): the product by a power of two is exact.
+__device__ __forceinline__ long long to_fixed(float v, double p2) { return __double2ll_rn(__dmul_rn((double)v, p2)); }
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  epoch += 1;
+  group_barrier(counter, epoch * gridDim.x);
+}
+
+// ------------------------------------------------------------------ prep
+__global__ void km_prep_max_kernel(const float* __restrict__ X, const int* __restrict__ n_ptr, int ld, int C, int k, KmWs ws) {
+  const int n = *n_ptr;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (n < k || n <= 0)) atomicMax(ws.status, 1);
+  const int f = blockIdx.y;
+  unsigned m = 0;
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float a = fabsf(__ldg(X + (size_t)f * ld + i));
+    if (!(a <= 3.0e38f)) bad = true;
+    m = max(m, __float_as_uint(a));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(ws.maxabs_bits, m);
+  if (bad) atomicMax(ws.status, 2);
+}
+
+__global__ void km_prep_sums_kernel(const float* __restrict__ X, const int* __restrict__ n_ptr, int ld, int C, KmWs ws) {
+  const int n = *n_ptr;
+  if (*ws.status) return;
+  const KmScales sc = km_scales(*ws.maxabs_bits, n, C);
+  const int f = blockIdx.y;
+  long long s = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    s += to_fixed(__ldg(X + (size_t)f * ld + i), sc.p_mean);
+  s = warp_sum_ll(s);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd((unsigned long long*)(ws.colsum + f), (unsigned long long)s);
+}
+
+__global__ void km_prep_center_kernel(const float* __restrict__ X, const int* __restrict__ n_ptr, int ld, int C, KmWs ws) {
+  const int n = *n_ptr;
+  if (*ws.status) return;
+  const KmScales sc = km_scales(*ws.maxabs_bits, n, C);
+  const int f = blockIdx.y;
+  const float mean = __double2float_rn(__ddiv_rn(__dmul_rn(__ll2double_rn(ws.colsum[f]), sc.ip_mean), (double)n));
+  if (blockIdx.x == 0 && threadIdx.x == 0) ws.mean[f] = mean;
+  long long t = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = __fsub_rn(__ldg(X + (size_t)f * ld + i), mean);
+    ws.Xc[(size_t)f * ld + i] = v;
+    t += to_fixed(__fmul_rn(v, v), sc.p_t);
+  }
+  t = warp_sum_ll(t);
+  if ((threadIdx.x & 31) == 0 && t) atomicAdd((unsigned long long*)ws.tolsum, (unsigned long long)t);
+}
+
+// centres handed in by the caller (array init): subtract the mean like KMeans.fit does.
+__global__ void km_init_centers_kernel(const float* __restrict__ init, int R, int k, int C, KmWs ws) {
+  if (*ws.status) return;
+  const int total = R * k * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    ws.centers[i] = __fsub_rn(init[i], ws.mean[i % C]);
+    if (i % C == 0) ws.seed_idx[i / C] = -1;
+  }
+}
+
+// ------------------------------------------------------------------ seeding
+template <int CP>
+__device__ __forceinline__ float sqdist_reg_smem(const float (&x)[CP], const float* __restrict__ c, int C) {
+  float acc = 0.f;
+#pragma unroll
+  for (int f = 0; f < CP; ++f)
+    if (f < C) { const float t = __fsub_rn(x[f], c[f]); acc = __fmaf_rn(t, t, acc); }
+  return acc;
+}
+
+// RandomState.choice(n, p=uniform): first i with fl64((i+1)/n) > u
+__device__ inline int first_center_index(double u, int n) {
+  long long i = __double2ll_rz(__dmul_rn(u, (double)n));
+  if (i > n - 1) i = n - 1;
+  if (i < 0) i = 0;
+  while (i > 0 && __ddiv_rn((double)i, (double)n) > u) --i;
+  while (i < n - 1 && __ddiv_rn((double)(i + 1), (double)n) <= u) ++i;
+  return (int)i;
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kSeedThreads, 1)
+km_seed_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, const double* __restrict__ uniforms, KmWs ws) {
+  const int n = *n_ptr;
+  if (*ws.status) return;
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kSeedThreads / 32;
+  const KmScales sc = km_scales(*ws.maxabs_bits, n, C);
+  const double* u = uniforms + (size_t)r * (1 + (k - 1) * L);
+  const float* __restrict__ Xc = ws.Xc;
+  float* __restrict__ closest = ws.closest + (size_t)r * ld;
+
+  __shared__ float s_cand[kMaxL][64];
+  __shared__ long long s_wtot[NW];       // per-warp-segment total of the current closest[]
+  __shared__ long long s_wpre[NW + 1];   // exclusive prefix over segments
+  __shared__ long long s_pot[NW][kMaxL];
+  __shared__ long long s_Tq[kMaxL];
+  __shared__ int s_cidx[kMaxL];
+  __shared__ int s_best;
+  __shared__ long long s_potcur;
+
+  const int seg = ((n + NW - 1) / NW + 31) / 32 * 32;  // points per warp segment, multiple of 32
+  const int seg_lo = warp * seg, seg_hi = min(n, seg_lo + seg);
+
+  // ---- first centre
+  if (threadIdx.x == 0) { s_cidx[0] = first_center_index(u[0], n); ws.seed_idx[(size_t)r * k] = s_cidx[0]; }
+  __syncthreads();
+  if (threadIdx.x < C) s_cand[0][threadIdx.x] = Xc[(size_t)threadIdx.x * ld + s_cidx[0]];
+  __syncthreads();
+  {
+    long long tot = 0;
+    for (int i = seg_lo + lane; i < seg_hi; i += 32) {
+      float x[CP];
+#pragma unroll
+      for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+      const float d = sqdist_reg_smem<CP>(x, s_cand[0], C);
+      closest[i] = d;
+      tot += to_fixed(d, sc.p_d);
+    }
+    tot = warp_sum_ll(tot);
+    if (lane == 0) s_wtot[warp] = tot;
+  }
+  __syncthreads();
+
+  for (int c = 1; c < k; ++c) {
+    if (threadIdx.x == 0) {
+      long long p = 0;
+      for (int w = 0; w < NW; ++w) { s_wpre[w] = p; p += s_wtot[w]; }
+      s_wpre[NW] = p;
+      s_potcur = p;
+    }
+    __syncthreads();
+    if (threadIdx.x < L) {
+      const double T = __dmul_rn(u[1 + (c - 1) * L + threadIdx.x], __ll2double_rn(s_potcur));
+      s_Tq[threadIdx.x] = __double2ll_ru(T);
+      s_cidx[threadIdx.x] = n - 1;  // np.clip(candidate_ids, None, n-1)
+    }
+    __syncthreads();
+    // searchsorted(cumsum, T, side='left'): the warp whose segment crosses T finds the index.
+    for (int t = 0; t < L; ++t) {
+      const long long Tq = s_Tq[t];
+      const long long lo = s_wpre[warp], hi = lo + s_wtot[warp];
+      // first segment whose inclusive prefix reaches Tq: lo < Tq <= hi, or Tq <= 0 for segment 0
+      const bool mine = (hi >= Tq) && (warp == 0 ? true : lo < Tq);
+      if (mine && seg_lo < n) {
+        long long base = lo;
+        for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
+          const int i = i0 + lane;
+          long long q = (i < seg_hi) ? to_fixed(closest[i], sc.p_d) : 0;
+          // inclusive warp scan
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, q, o);
+            if (lane >= o) q += y;
+          }
+          const long long pre = base + q;
+          const unsigned hit = __ballot_sync(0xffffffffu, (i < seg_hi) && pre >= Tq);
+          if (hit) {
+            if (lane == 0) s_cidx[t] = i0 + (__ffs(hit) - 1);
+            break;
+          }
+          base += __shfl_sync(0xffffffffu, q, 31);
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < L * C; idx += kSeedThreads) {
+      const int t = idx / C, f = idx % C;
+      s_cand[t][f] = Xc[(size_t)f * ld + s_cidx[t]];
+    }
+    __syncthreads();
+    // pass 1: potential of every candidate
+    long long pot[kMaxL];
+#pragma unroll
+    for (int t = 0; t < kMaxL; ++t) pot[t] = 0;
+    for (int i = seg_lo + lane; i < seg_hi; i += 32) {
+      float x[CP];
+#pragma unroll
+      for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+      const float cl = closest[i];
+#pragma unroll
+      for (int t = 0; t < kMaxL; ++t)
+        if (t < L) pot[t] += to_fixed(fminf(cl, sqdist_reg_smem<CP>(x, s_cand[t], C)), sc.p_d);
+    }
+#pragma unroll
+    for (int t = 0; t < kMaxL; ++t)
+      if (t < L) {
+        const long long v = warp_sum_ll(pot[t]);
+        if (lane == 0) s_pot[warp][t] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int best = 0;
+      long long bp = 0;
+      for (int t = 0; t < L; ++t) {
+        long long p = 0;
+        for (int w = 0; w < NW; ++w) p += s_pot[w][t];
+        if (t == 0 || p < bp) { bp = p; best = t; }
+      }
+      s_best = best;
+      ws.seed_idx[(size_t)r * k + c] = s_cidx[best];
+    }
+    __syncthreads();
+    // pass 2: closest = min(closest, d(best)), new segment totals
+    {
+      const int b = s_best;
+      long long tot = 0;
+      for (int i = seg_lo + lane; i < seg_hi; i += 32) {
+        float x[CP];
+#pragma unroll
+        for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+        const float nd = fminf(closest[i], sqdist_reg_smem<CP>(x, s_cand[b], C));
+        closest[i] = nd;
+        tot += to_fixed(nd, sc.p_d);
+      }
+      tot = warp_sum_ll(tot);
+      if (lane == 0) s_wtot[warp] = tot;
+    }
+    __syncthreads();
+  }
+  // centres of this restart = the picked rows
+  for (int idx = threadIdx.x; idx < k * C; idx += kSeedThreads) {
+    const int j = idx / C, f = idx % C;
+    ws.centers[((size_t)r * k + j) * C + f] = Xc[(size_t)f * ld + ws.seed_idx[(size_t)r * k + j]];
+  }
+}
+
+// ------------------------------------------------------------------ Lloyd
+struct LloydParams {
+  const int* n_ptr;
+  int ld, C, k, R, max_iter;
+  double tol_rel;
+  KmWs ws;
+  int* labels_out;      // [ld] int32
+  float* centers_out;   // [k][C]
+  double* inertia_out;  // [R]
+  int* n_iter_out;      // [R]
+  int* info;            // [4] status, best restart, n, total Lloyd iterations
+};
+
+// E-step of one tile: labels of kPPT points per thread against the centres in smem.
+template <int CP>
+__device__ __forceinline__ void estep_tile(const float* __restrict__ Xc, int ld, int n, int C, int k, int tile,
+                                           const float* __restrict__ s_cent, const float* __restrict__ s_csq, int (&lab)[kPPT],
+                                           float (&x)[kPPT][CP]) {
+  const int base = tile * kTile + threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < kPPT; ++p) {
+    const int i = base + p * kLloydThreads;
+#pragma unroll
+    for (int f = 0; f < CP; ++f) x[p][f] = (f < C && i < n) ? Xc[(size_t)f * ld + i] : 0.f;
+  }
+  float bv[kPPT];
+#pragma unroll
+  for (int p = 0; p < kPPT; ++p) { bv[p] = 0.f; lab[p] = 0; }
+  for (int j = 0; j < k; ++j) {
+    const float* __restrict__ c = s_cent + j * CP;
+    float dot[kPPT];
+#pragma unroll
+    for (int p = 0; p < kPPT; ++p) dot[p] = 0.f;
+#pragma unroll
+    for (int f4 = 0; f4 < CP; f4 += 4) {
+      const float4 cv = *reinterpret_cast<const float4*>(c + f4);
+#pragma unroll
+      for (int p = 0; p < kPPT; ++p) {
+        // zero padding beyond C is exact: fmaf(0, 0, acc) == acc
+        dot[p] = __fmaf_rn(x[p][f4 + 0], cv.x, dot[p]);
+        dot[p] = __fmaf_rn(x[p][f4 + 1], cv.y, dot[p]);
+        dot[p] = __fmaf_rn(x[p][f4 + 2], cv.z, dot[p]);
+        dot[p] = __fmaf_rn(x[p][f4 + 3], cv.w, dot[p]);
+      }
+    }
+    const float cs = s_csq[j];
+#pragma unroll
+    for (int p = 0; p < kPPT; ++p) {
+      const float v = __fmaf_rn(-2.f, dot[p], cs);
+      if (j == 0 || v < bv[p]) { bv[p] = v; lab[p] = j; }
+    }
+  }
+}
+
+__device__ __forceinline__ void load_centers(const float* __restrict__ gc, float* s_cent, float* s_csq, int k, int C, int CP) {
+  for (int idx = threadIdx.x; idx < k * CP; idx += kLloydThreads) {
+    const int j = idx / CP, f = idx % CP;
+    s_cent[idx] = (f < C) ? __ldcg(gc + (size_t)j * C + f) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += kLloydThreads) {
+    float a = 0.f;
+    for (int f = 0; f < C; ++f) a = __fmaf_rn(s_cent[j * CP + f], s_cent[j * CP + f], a);
+    s_csq[j] = a;
+  }
+  __syncthreads();
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = *prm.n_ptr;
+  const int C = prm.C, k = prm.k, R = prm.R, ld = prm.ld;
+  const KmWs& ws = prm.ws;
+  const int status = *ws.status;
+  if (status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { prm.info[0] = status; prm.info[1] = 0; prm.info[2] = n; prm.info[3] = 0; }
+    return;
+  }
+  float* s_cent = reinterpret_cast<float*>(smem_raw);                       // [k][CP]
+  float* s_csq = s_cent + k * CP;                                           // [k]
+  long long* s_sums = reinterpret_cast<long long*>(s_csq + ((k + 3) / 4 * 4 + 2) / 2 * 2);  // [k][C] (8B aligned)
+  int* s_cnt = reinterpret_cast<int*>(s_sums + (size_t)k * C);             // [k]
+  __shared__ int s_active[kMaxInit];
+  __shared__ int s_nactive;
+  __shared__ long long s_redll[kLloydThreads / 32];
+  __shared__ float s_redf[kLloydThreads / 32];
+  __shared__ int s_redi[kLloydThreads / 32];
+  __shared__ int s_misc[4];
+
+  const KmScales sc = km_scales(*ws.maxabs_bits, n, C);
+  const float tol_abs = __double2float_rn(__dmul_rn(__ddiv_rn(__dmul_rn(__ll2double_rn(*ws.tolsum), sc.ip_t),
+                                                               __dmul_rn((double)n, (double)C)), prm.tol_rel));
+  const int tiles = (n + kTile - 1) / kTile;
+  const float* __restrict__ Xc = ws.Xc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned epoch = 0;
+  int total_iters = 0;
+
+  auto zero_acc = [&]() {
+    for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) s_sums[idx] = 0;
+    for (int j = threadIdx.x; j < k; j += kLloydThreads) s_cnt[j] = 0;
+  };
+  auto flush_acc = [&](int r) {
+    for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) {
+      const long long v = s_sums[idx];
+      if (v) atomicAdd((unsigned long long*)(ws.sums + (size_t)r * k * C + idx), (unsigned long long)v);
+    }
+    for (int j = threadIdx.x; j < k; j += kLloydThreads) {
+      const int v = s_cnt[j];
+      if (v) atomicAdd(ws.cnt + (size_t)r * k + j, v);
+    }
+  };
+
+  // mode 0: Lloyd E-step with incremental M-step; mode 1: labels only (E-step re-run)
+  auto run_estep = [&](int mode) {
+    const int total = s_nactive * tiles;
+    const int ipc = (total + gridDim.x - 1) / gridDim.x;
+    const int it0 = blockIdx.x * ipc, it1 = min(total, it0 + ipc);
+    int cur = -1;
+    for (int item = it0; item < it1; ++item) {
+      const int r = s_active[item / tiles], tile = item % tiles;
+      if (r != cur) {
+        if (cur >= 0 && mode == 0) { __syncthreads(); flush_acc(cur); }
+        __syncthreads();
+        load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP);
+        if (mode == 0) zero_acc();
+        __syncthreads();
+        cur = r;
+      }
+      int lab[kPPT];
+      float x[kPPT][CP];
+      estep_tile<CP>(Xc, ld, n, C, k, tile, s_cent, s_csq, lab, x);
+      unsigned char* labels = ws.labels + (size_t)r * ld;
+      unsigned char* acct = ws.acct + (size_t)r * ld;
+      bool any_changed = false;
+#pragma unroll
+      for (int p = 0; p < kPPT; ++p) {
+        const int i = tile * kTile + p * kLloydThreads + threadIdx.x;
+        if (i < n) {
+          const int l = lab[p];
+          const int lp = labels[i];
+          if (mode == 0) {
+            const int a = acct[i];
+            if (l != a) {
+#pragma unroll
+              for (int f = 0; f < CP; ++f)
+                if (f < C) {
+                  const long long q = to_fixed(x[p][f], sc.p_x);
+                  if (a != 255) atomicAdd((unsigned long long*)(s_sums + a * C + f), (unsigned long long)(-q));
+                  atomicAdd((unsigned long long*)(s_sums + l * C + f), (unsigned long long)q);
+                }
+              if (a != 255) atomicSub(s_cnt + a, 1);
+              atomicAdd(s_cnt + l, 1);
+              acct[i] = (unsigned char)l;
+            }
+          }
+          if (l != lp) { labels[i] = (unsigned char)l; any_changed = true; }
+        }
+      }
+      if (mode == 0 && __syncthreads_or(any_changed) && threadIdx.x == 0) ws.changed[r] = 1;
+    }
+    if (cur >= 0 && mode == 0) { __syncthreads(); flush_acc(cur); }
+  };
+
+  auto rebuild_active = [&](int want_mode) {
+    // want_mode 0: state==0 (still iterating); 1: finished without strict convergence; 2: all
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int m = 0;
+      for (int r = 0; r < R; ++r) {
+        const int st = __ldcg(ws.state + r);
+        if ((want_mode == 0 && st == 0) || (want_mode == 1 && st == 2) || want_mode == 2) s_active[m++] = r;
+      }
+      s_nactive = m;
+    }
+    __syncthreads();
+  };
+
+  // labels / acct start as "none" (255)
+  for (size_t idx = (size_t)blockIdx.x * kLloydThreads + threadIdx.x; idx < (size_t)R * ld; idx += (size_t)gridDim.x * kLloydThreads) {
+    ws.labels[idx] = 255;
+    ws.acct[idx] = 255;
+  }
+  grid_barrier(ws.barrier, epoch);
+
+  for (int it = 0; it < prm.max_iter; ++it) {
+    rebuild_active(0);
+    if (s_nactive == 0) break;
+    ++total_iters;
+    run_estep(0);
+    grid_barrier(ws.barrier, epoch);
+
+    // ---- per-restart update: one CTA per active restart
+    for (int a = blockIdx.x; a < s_nactive; a += gridDim.x) {
+      const int r = s_active[a];
+      long long* gs = ws.sums + (size_t)r * k * C;
+      int* gc = ws.cnt + (size_t)r * k;
+      float* cen = ws.centers + (size_t)r * k * C;
+      unsigned char* labels = ws.labels + (size_t)r * ld;
+      unsigned char* acct = ws.acct + (size_t)r * ld;
+      // empty clusters (list fixed before any point moves)
+      __shared__ int s_empty[kMaxK + 2];
+      __shared__ int s_nempty;
+      if (threadIdx.x == 0) {
+        int m = 0;
+        for (int j = 0; j < k; ++j)
+          if (__ldcg(gc + j) == 0) s_empty[m++] = j;
+        s_nempty = m;
+      }
+      __syncthreads();
+      if (s_nempty > 0) {
+        // old centres are still in ws.centers; distances of every point to its assigned centre
+        load_centers(cen, s_cent, s_csq, k, C, CP);
+        __shared__ int s_taken[kMaxK + 2];
+        for (int e = 0; e < s_nempty; ++e) {
+          float bd = -1.f;
+          int bi = 0x7fffffff;
+          for (int i = threadIdx.x; i < n; i += kLloydThreads) {
+            bool taken = false;
+            for (int q = 0; q < e; ++q) taken |= (s_taken[q] == i);
+            if (taken) continue;
+            const float* c = s_cent + (int)labels[i] * CP;
+            float acc = 0.f;
+            for (int f = 0; f < C; ++f) { const float t = __fsub_rn(Xc[(size_t)f * ld + i], c[f]); acc = __fmaf_rn(t, t, acc); }
+            if (acc > bd) { bd = acc; bi = i; }  // ascending i per thread: lowest index wins ties
+          }
+          // block arg-max on (distance desc, index asc)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+          }
+          if (lane == 0) { s_redf[warp] = bd; s_redi[warp] = bi; }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            float fd = s_redf[0]; int fi = s_redi[0];
+            for (int w = 1; w < kLloydThreads / 32; ++w)
+              if (s_redf[w] > fd || (s_redf[w] == fd && s_redi[w] < fi)) { fd = s_redf[w]; fi = s_redi[w]; }
+            s_misc[0] = fi;
+            s_misc[1] = (e == 0 && !(fd > 0.f)) ? 1 : 0;  // max distance 0: relocation is pointless
+            s_taken[e] = fi;
+          }
+          __syncthreads();
+          if (s_misc[1] || s_misc[0] == 0x7fffffff) break;
+          const int far = s_misc[0];
+          const int j = s_empty[e];
+          const int old = acct[far];
+          for (int f = threadIdx.x; f < C; f += kLloydThreads) {
+            const long long q = to_fixed(Xc[(size_t)f * ld + far], sc.p_x);
+            gs[(size_t)old * C + f] -= q;
+            gs[(size_t)j * C + f] = q;
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) { gc[old] -= 1; gc[j] = 1; acct[far] = (unsigned char)j; }
+          __syncthreads();
+        }
+      }
+      // new centres
+      float* s_new = s_cent;  // reuse [k][CP] (old centres are read from global below)
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) {
+        const int j = idx / C, f = idx % C;
+        const int cj = gc[j];
+        if (cj > 0) s_new[j * CP + f] = __double2float_rn(__ddiv_rn(__dmul_rn(__ll2double_rn(gs[idx]), sc.ip_x), (double)cj));
+      }
+      if (threadIdx.x == 0) {
+        int amax = 0;
+        for (int j = 1; j < k; ++j)
+          if (gc[j] > gc[amax]) amax = j;
+        s_misc[2] = amax;
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) {
+        const int j = idx / C, f = idx % C;
+        if (gc[j] <= 0) s_new[j * CP + f] = s_new[s_misc[2] * CP + f];
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < k; j += kLloydThreads) {
+        float acc = 0.f;
+        for (int f = 0; f < C; ++f) { const float t = __fsub_rn(s_new[j * CP + f], cen[(size_t)j * C + f]); acc = __fmaf_rn(t, t, acc); }
+        s_csq[j] = __fsqrt_rn(acc);
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) cen[idx] = s_new[(idx / C) * CP + idx % C];
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int j = 0; j < k; ++j) tot = __fmaf_rn(s_csq[j], s_csq[j], tot);
+        const int changed = __ldcg(ws.changed + r);
+        ws.changed[r] = 0;
+        int st = 0;
+        if (!changed) st = 1;
+        else if (tot <= tol_abs) st = 2;
+        else if (it + 1 >= prm.max_iter) st = 2;
+        if (st) { ws.state[r] = st; ws.n_iter[r] = it + 1; }
+      }
+      __syncthreads();
+    }
+    grid_barrier(ws.barrier, epoch);
+  }
+
+  // ---- E-step re-run for restarts that did not converge strictly
+  rebuild_active(1);
+  if (s_nactive > 0) run_estep(1);
+  grid_barrier(ws.barrier, epoch);
+
+  // ---- inertia of every restart (direct-form distances, exact fixed-point sum)
+  rebuild_active(2);
+  {
+    const int total = R * tiles;
+    const int ipc = (total + gridDim.x - 1) / gridDim.x;
+    const int it0 = blockIdx.x * ipc, it1 = min(total, it0 + ipc);
+    int cur = -1;
+    long long acc = 0;
+    auto flush_inertia = [&](int r) {
+      long long v = warp_sum_ll(acc);
+      if (lane == 0) s_redll[warp] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < kLloydThreads / 32; ++w) t += s_redll[w];
+        if (t) atomicAdd((unsigned long long*)(ws.inertia_q + r), (unsigned long long)t);
+      }
+      __syncthreads();
+      acc = 0;
+    };
+    for (int item = it0; item < it1; ++item) {
+      const int r = item / tiles, tile = item % tiles;
+      if (r != cur) {
+        if (cur >= 0) flush_inertia(cur);
+        __syncthreads();
+        load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP);
+        cur = r;
+      }
+      const unsigned char* labels = ws.labels + (size_t)r * ld;
+#pragma unroll
+      for (int p = 0; p < kPPT; ++p) {
+        const int i = tile * kTile + p * kLloydThreads + threadIdx.x;
+        if (i < n) {
+          const float* c = s_cent + (int)labels[i] * CP;
+          float d = 0.f;
+          for (int f = 0; f < C; ++f) { const float t = __fsub_rn(Xc[(size_t)f * ld + i], c[f]); d = __fmaf_rn(t, t, d); }
+          acc += to_fixed(d, sc.p_d);
+        }
+      }
+    }
+    if (cur >= 0) flush_inertia(cur);
+  }
+  grid_barrier(ws.barrier, epoch);
+
+  // ---- best restart: lowest inertia unless it is the same clustering (KMeans.fit, _kmeans.py:1534-1541)
+  if (blockIdx.x == 0) {
+    __shared__ int s_mapmin[256], s_mapmax[256];
+    int best = 0;
+    for (int r = 1; r < R; ++r) {
+      if (__ldcg(ws.inertia_q + r) < __ldcg(ws.inertia_q + best)) {
+        for (int j = threadIdx.x; j < 256; j += kLloydThreads) { s_mapmin[j] = 0x7fffffff; s_mapmax[j] = -1; }
+        __syncthreads();
+        const unsigned char* l1 = ws.labels + (size_t)r * ld;
+        const unsigned char* l2 = ws.labels + (size_t)best * ld;
+        for (int i = threadIdx.x; i < n; i += kLloydThreads) {
+          const int a = l1[i], b = l2[i];
+          if (s_mapmin[a] > b) atomicMin(&s_mapmin[a], b);
+          if (s_mapmax[a] < b) atomicMax(&s_mapmax[a], b);
+        }
+        __syncthreads();
+        const int bad = __syncthreads_or(threadIdx.x < 256 && s_mapmax[threadIdx.x] >= 0 && s_mapmin[threadIdx.x] != s_mapmax[threadIdx.x]);
+        if (bad) best = r;  // not the same clustering -> take the better restart
+      }
+    }
+    const unsigned char* lb = ws.labels + (size_t)best * ld;
+    for (int i = threadIdx.x; i < n; i += kLloydThreads) prm.labels_out[i] = lb[i];
+    for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads)
+      prm.centers_out[idx] = __fadd_rn(ws.centers[(size_t)best * k * C + idx], ws.mean[idx % C]);
+    for (int r = threadIdx.x; r < R; r += kLloydThreads) {
+      prm.inertia_out[r] = __dmul_rn(__ll2double_rn(ws.inertia_q[r]), sc.ip_d);
+      prm.n_iter_out[r] = ws.n_iter[r];
+    }
+    if (threadIdx.x == 0) { prm.info[0] = 0; prm.info[1] = best; prm.info[2] = n; prm.info[3] = total_iters; }
+  }
+}
+
+size_t lloyd_smem_bytes(int k, int C, int CP) {
+  size_t fl = (size_t)k * CP + ((k + 3) / 4 * 4 + 2) / 2 * 2;
+  return fl * 4 + (size_t)k * C * 8 + (size_t)k * 4 + 16;
+}
+
+template <int CP>
+int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, cudaStream_t stream) {
+  km_seed_kernel<CP><<<R, kSeedThreads, 0, stream>>>(n_ptr, ld, C, k, L, uniforms, ws);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+template <int CP>
+int launch_lloyd(const LloydParams& prm, int num_sms, cudaStream_t stream) {
+  const size_t smem = lloyd_smem_bytes(prm.k, prm.C, CP);
+  const void* fn = (const void*)km_lloyd_kernel<CP>;
+  if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLloydThreads, smem));
+  ISA_CHECK_ARG(occ >= 1, "kmeans: Lloyd kernel does not fit on an SM (smem %zu)", smem);
+  if (occ > 2) occ = 2;
+  void* args[] = {(void*)&prm};
+  ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms * occ), dim3(kLloydThreads), args, smem, stream));
+  return ISA_OK;
+}
+
+int pick_cp(int C) { return C <= 8 ? 8 : C <= 16 ? 16 : C <= 24 ? 24 : C <= 32 ? 32 : 64; }
+
+}  // namespace
+
+extern "C" {
+
+size_t isa_kmeans_workspace_bytes(int ld, int C, int k, int n_init) {
+  if (ld <= 0 || C <= 0 || k <= 0 || n_init <= 0) return 0;
+  return km_carve(nullptr, ld, C, k, n_init).total_bytes;
+}
+
+int isa_kmeans_fit(const float* X, const int* n_ptr, int ld, int C, int k, int n_init, int max_iter, double tol_rel,
+                   int n_local_trials, const double* uniforms, const float* init_centers,
+                   int* labels_out, float* centers_out, double* inertia_out, int* n_iter_out, int* seed_idx_out, int* info,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ISA_CHECK_ARG(X && n_ptr && labels_out && centers_out && inertia_out && n_iter_out && info && workspace, "kmeans_fit: null pointer");
+  ISA_CHECK_ARG(uniforms || init_centers, "kmeans_fit: need either the uniforms of the k-means++ stream or init_centers");
+  ISA_CHECK_ARG(ld > 0 && C > 0 && C <= 64, "kmeans_fit: need 0 < C <= 64 (got C=%d, ld=%d)", C, ld);
+  ISA_CHECK_ARG(k > 0 && k <= kMaxK, "kmeans_fit: need 0 < k <= %d (uint8 instance mask), got %d", kMaxK, k);
+  ISA_CHECK_ARG(n_init > 0 && n_init <= kMaxInit, "kmeans_fit: need 0 < n_init <= %d, got %d", kMaxInit, n_init);
+  ISA_CHECK_ARG(max_iter > 0, "kmeans_fit: max_iter must be positive");
+  ISA_CHECK_ARG(n_local_trials > 0 && n_local_trials <= kMaxL, "kmeans_fit: n_local_trials %d not in 1..%d", n_local_trials, kMaxL);
+  KmWs ws = km_carve(workspace, ld, C, k, n_init);
+  if (workspace_bytes < ws.total_bytes) {
+    isa_set_error("kmeans_fit: workspace %zu < required %zu bytes", workspace_bytes, ws.total_bytes);
+    return ISA_ERR_WORKSPACE;
+  }
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  ISA_CUDA(cudaMemsetAsync(workspace, 0, ws.zero_bytes, stream));
+  int gx = (ld + 255) / 256;
+  const int cap = (di.num_sms * 8 + C - 1) / C;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, C);
+  km_prep_max_kernel<<<grid, 256, 0, stream>>>(X, n_ptr, ld, C, k, ws);
+  km_prep_sums_kernel<<<grid, 256, 0, stream>>>(X, n_ptr, ld, C, ws);
+  km_prep_center_kernel<<<grid, 256, 0, stream>>>(X, n_ptr, ld, C, ws);
+  ISA_CUDA(cudaGetLastError());
+  const int CP = pick_cp(C);
+  if (init_centers) {
+    km_init_centers_kernel<<<(n_init * k * C + 255) / 256, 256, 0, stream>>>(init_centers, n_init, k, C, ws);
+    ISA_CUDA(cudaGetLastError());
+  } else {
+    switch (CP) {
+      case 8: rc = launch_seed<8>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
+      case 16: rc = launch_seed<16>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
+      case 24: rc = launch_seed<24>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
+      case 32: rc = launch_seed<32>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
+      default: rc = launch_seed<64>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
+    }
+    if (rc) return rc;
+  }
+  LloydParams prm;
+  prm.n_ptr = n_ptr; prm.ld = ld; prm.C = C; prm.k = k; prm.R = n_init; prm.max_iter = max_iter; prm.tol_rel = tol_rel;
+  prm.ws = ws; prm.labels_out = labels_out; prm.centers_out = centers_out; prm.inertia_out = inertia_out;
+  prm.n_iter_out = n_iter_out; prm.info = info;
+  switch (CP) {
+    case 8: rc = launch_lloyd<8>(prm, di.num_sms, stream); break;
+    case 16: rc = launch_lloyd<16>(prm, di.num_sms, stream); break;
+    case 24: rc = launch_lloyd<24>(prm, di.num_sms, stream); break;
+    case 32: rc = launch_lloyd<32>(prm, di.num_sms, stream); break;
+    default: rc = launch_lloyd<64>(prm, di.num_sms, stream); break;
+  }
+  if (rc) return rc;
+  if (seed_idx_out) ISA_CUDA(cudaMemcpyAsync(seed_idx_out, ws.seed_idx, sizeof(int) * (size_t)n_init * k, cudaMemcpyDeviceToDevice, stream));
+  return ISA_OK;
+}
+
+}  // extern "C"
