@@ -117,6 +117,32 @@ int isa_scatter_labels_upsample(const int* labels, const int* fg_index, const in
                                 unsigned char* ins_small, unsigned char* ins_up, unsigned char* cls_up,
                                 isa_stream_t stream);
 
+/* ------------------------------------------------------------------ ReNet bidirectional-GRU sweeps
+ * Replaces the recurrent part of ReNet's rnn_hor / rnn_ver (nn.GRU, bidirectional):
+ *   /root/reference/code/lib/archs/modules/README.md:225-256 (contract; renet.py is absent from the tree,
+ *   the arithmetic is PyTorch's nn.GRU: r,z = sigmoid(..), n = tanh(W_in x + b_in + r*(W_hn h + b_hn)),
+ *   h' = (1-z)*n + z*h, weight_hh_l0 (3n, n) in gate order r,z,n).
+ * All tensors are token-major ("channels last"):
+ *   gx    [tokens][2][3n]  x W_ih^T + b_ih of both directions (one library GEMM by the caller)
+ *   w_hh  [2][3n][n], b_hh [2][3n]
+ *   out   [tokens][2n]     h_t of direction 0 in [0,n), of direction 1 (reverse sweep) in [n,2n)
+ *   stash [tokens][2][4n]  r, z, n, (W_hn h + b_hn) kept for backward, or NULL for inference
+ * Sequence q (0 <= q < n_seq) at step t lives at token
+ *   (q / inner) * outer_tok_stride + (q % inner) * inner_tok_stride + t * t_tok_stride,
+ * so a row sweep over [B][H][W] is (n_seq=B*H, T=W, inner=B*H, 0, W, 1) and a column sweep is
+ * (n_seq=B*W, T=H, inner=W, H*W, 1, W).  h_0 = 0.  n_units: multiple of 4, <= 128.
+ * Backward writes dgx [tokens][2][3n] (gradient of the input projection; its r,z thirds are also the
+ * hidden-side gate gradients) and dghn [tokens][2][n] (hidden-side n-gate gradient r*dn_pre);
+ * weight/bias gradients are GEMMs / column sums over those (done by the caller). */
+int isa_gru_scan_fwd(const float* gx, const float* w_hh, const float* b_hh, int n_seq, int T, int n_units,
+                     int inner, long long outer_tok_stride, long long inner_tok_stride, long long t_tok_stride,
+                     float* out, float* stash, isa_stream_t stream);
+
+int isa_gru_scan_bwd(const float* dout, const float* out, const float* stash, const float* w_hh,
+                     int n_seq, int T, int n_units,
+                     int inner, long long outer_tok_stride, long long inner_tok_stride, long long t_tok_stride,
+                     float* dgx, float* dghn, isa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ c_float = ctypes.c_float
 c_size_t = ctypes.c_size_t
 c_uint64 = ctypes.c_uint64
 c_double = ctypes.c_double
+c_longlong = ctypes.c_longlong
 
 # name -> (restype, argtypes); kept in the order of include/isa_b200.h
 SIGNATURES = {
@@ -54,6 +55,13 @@ SIGNATURES = {
                                c_void_p, c_size_t, c_void_p]),
     "isa_scatter_labels_upsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    # ReNet GRU scan
+    "isa_gru_scan_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_longlong, c_longlong, c_longlong,
+                                 c_void_p, c_void_p, c_void_p]),
+    "isa_gru_scan_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_longlong, c_longlong, c_longlong,
+                                 c_void_p, c_void_p, c_void_p]),
 }
 
 

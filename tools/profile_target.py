@@ -1,0 +1,37 @@
+"""Short deterministic workload for ncu: python tools/profile_target.py [disc|kmeans|all]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from isa_b200 import clustering, synth  # noqa: E402
+from isa_b200.losses import DiscriminativeLoss  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = torch.device("cuda:0")
+if what in ("disc", "all"):
+    d = synth.batch(0, 16, 24, 256, 256, 32)
+    x = torch.tensor(d["emb"], device=dev, requires_grad=True)
+    lab = torch.tensor(d["labels"], device=dev)
+    n = torch.tensor(d["n_objects"], device=dev)
+    crit = DiscriminativeLoss(0.5, 1.5, 2)
+    for _ in range(3):
+        loss, _ = crit(x, lab, n, 32)
+        loss.backward()
+    torch.cuda.synchronize()
+    print("disc loss", float(loss))
+if what in ("kmeans", "all"):
+    rs = np.random.RandomState(0)
+    k, C, nn = 16, 24, 40000
+    cent = rs.standard_normal((k, C))
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    X = (0.3 * rs.standard_normal((nn, C)) + 0.7 * cent[rs.randint(0, k, nn)]).astype(np.float32)
+    Xt = torch.tensor(X, device=dev).t().contiguous()
+    n_dev = torch.tensor([nn], device=dev, dtype=torch.int32)
+    for _ in range(2):
+        res = clustering.kmeans_fit(Xt, n_dev, k, seed=0, n_init=35)
+    torch.cuda.synchronize()
+    print("kmeans iters", int(res.n_iter.sum()))
