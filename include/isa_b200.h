@@ -117,6 +117,34 @@ int isa_scatter_labels_upsample(const int* labels, const int* fg_index, const in
                                 unsigned char* ins_small, unsigned char* ins_up, unsigned char* cls_up,
                                 isa_stream_t stream);
 
+/* ------------------------------------------------------------------ dense attention
+ * Replaces ScaledDotProductAttention.forward (+ autograd backward):
+ *   /root/reference/code/lib/archs/modules/utils.py:305-329
+ *     attn = softmax(masked_fill(q k^T / temperature, -inf), dim=2); out = attn v
+ * as called by MultiHeadAttention.forward (utils.py:193-225) with q,k,v already split per head:
+ *   q [BH][Lq][d], k [BH][Lk][d], v [BH][Lk][dv] f32, BH = n_head*batch (head-major), d, dv <= 16.
+ * Masks are u8, 1 = masked: key_mask [n_mask_rows][Lk] (broadcast over queries) and/or
+ * full_mask [n_mask_rows][Lq][Lk]; row used for head-batch bh is bh % n_mask_rows, which equals the
+ * reference's mask.repeat(n_head,1,1) without the copy.  A fully masked row yields NaN like the reference.
+ * out [BH][Lq][dv]; lse2 [BH][Lq] = log2-sum-exp2 of the scaled scores (needed by bwd / probs; may be NULL).
+ * Forward is a tcgen05 (TMEM accumulator) kernel fed by TMA bulk copies; operands are split into
+ * bf16 hi+lo so products are fp32-accurate.  The L_q x L_k probabilities are produced only by
+ * isa_attention_probs. */
+size_t isa_attention_workspace_bytes(int BH, int Lq, int Lk);
+
+int isa_attention_fwd(const float* q, const float* k, const float* v, int BH, int Lq, int Lk, int d, int dv, float temperature,
+                      const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                      float* out, float* lse2, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+int isa_attention_probs(const float* q, const float* k, const float* lse2, int BH, int Lq, int Lk, int d, float temperature,
+                        const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows, float* attn,
+                        isa_stream_t stream);
+
+int isa_attention_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout, const float* lse2,
+                      int BH, int Lq, int Lk, int d, int dv, float temperature,
+                      const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                      float* dq, float* dk, float* dv_out, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
 /* ------------------------------------------------------------------ ReNet bidirectional-GRU sweeps
  * Replaces the recurrent part of ReNet's rnn_hor / rnn_ver (nn.GRU, bidirectional):
  *   /root/reference/code/lib/archs/modules/README.md:225-256 (contract; renet.py is absent from the tree,

@@ -55,6 +55,16 @@ SIGNATURES = {
                                c_void_p, c_size_t, c_void_p]),
     "isa_scatter_labels_upsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    # dense attention
+    "isa_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "isa_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_attention_probs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "isa_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_int, c_float,
+                                  c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     # ReNet GRU scan
     "isa_gru_scan_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_longlong, c_longlong, c_longlong,

@@ -50,6 +50,7 @@ class _GruSweepFn(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(x2, w_ih, w_hh_c, out, stash)
             ctx.geom = (B, H, W, mode, n)
+            ctx.x_shape = tuple(x.shape)
         return out
 
     @staticmethod
@@ -89,7 +90,7 @@ class _GruSweepFn(torch.autograd.Function):
             dw_hh[d, 2 * n:] = g_n.t() @ hp
             db_hh[d, :2 * n] = g_rz.sum(0)
             db_hh[d, 2 * n:] = g_n.sum(0)
-        return dx.view(tokens, -1) if dx is not None else None, dw_ih, dw_hh, db_ih, db_hh, None, None, None, None
+        return dx.view(ctx.x_shape) if dx is not None else None, dw_ih, dw_hh, db_ih, db_hh, None, None, None, None
 
 
 def _stack_gru(gru):

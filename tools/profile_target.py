@@ -35,3 +35,15 @@ if what in ("kmeans", "all"):
         res = clustering.kmeans_fit(Xt, n_dev, k, seed=0, n_init=35)
     torch.cuda.synchronize()
     print("kmeans iters", int(res.n_iter.sum()))
+if what in ("renet",):
+    from isa_b200.renet import ReNet
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    mod = ReNet(256, 100).to(dev)
+    x = torch.randn(B, 256, 64, 64, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for _ in range(2):
+        y = mod(x)
+        y.backward(torch.ones_like(y))
+    torch.cuda.synchronize()
+    print("renet", float(y.sum()))
