@@ -45,6 +45,9 @@ int isa_num_sms(int* out);
  *            i.e. exactly what the reference's collate hands over (lib/dataset.py:354-376)
  * n_objects  [bs] i32 (device)
  * w_*        weights of the four terms; the shipped composite is (1, 0, 0, 0.005)
+ * q_den      NULL, or a device float overriding the q-regulariser denominator int(sum(target)) of
+ *            discriminative.py:153-159 (data parallel: global foreground count / world size, so that
+ *            the rank-averaged loss equals the single-process loss of the whole batch)
  * out_loss [1], out_terms [4] = unweighted (var, dist, reg, qreg), out_means [bs][K][C]
  * workspace  isa_disc_loss_workspace_bytes(bs,C,K) bytes; hand the SAME buffer, untouched,
  *            to isa_disc_loss_bwd (it carries the per-instance sums saved for backward).
@@ -60,7 +63,7 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
                       int bs, int C, int H, int W, int K,
                       float delta_v, float delta_d, int norm, int normalize_means,
                       float w_var, float w_dist, float w_reg, float w_q,
-                      float* out_loss, float* out_terms, float* out_means,
+                      const float* q_den, float* out_loss, float* out_terms, float* out_means,
                       void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 /* grad_loss [1] f32 (device), grad_means [bs][K][C] or NULL, grad_emb [bs][C][H][W] out. */
@@ -68,7 +71,7 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
                       int bs, int C, int H, int W, int K,
                       float delta_v, float delta_d, int norm, int normalize_means,
                       float w_var, float w_dist, float w_reg, float w_q,
-                      const float* means, const float* grad_loss, const float* grad_means,
+                      const float* q_den, const float* means, const float* grad_loss, const float* grad_means,
                       float* grad_emb, void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 /* Dense one-hot masks (kind 1..3) -> u8 label map; *not_onehot_flag (device int) is set to 1

@@ -33,13 +33,13 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_float, c_int, c_int,
                                   c_float, c_float, c_float, c_float,
-                                  c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "isa_disc_loss_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_float, c_int, c_int,
                                   c_float, c_float, c_float, c_float,
-                                  c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_onehot_to_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),

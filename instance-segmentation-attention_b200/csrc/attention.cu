@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
       }
       l_run = l_run * alpha + l_tile;
       // rescale the running output (previous PV MMAs are complete: s_full was committed after them)
-      if (j > 0 && alpha != 1.f) {
+      // tcgen05.ld/st are warp-collective (.sync.aligned): the branch must be warp-uniform
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         float o[16];
         tmem_ld16(t_row + kTmemO, o);
 #pragma unroll

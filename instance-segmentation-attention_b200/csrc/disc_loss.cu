@@ -98,6 +98,7 @@ struct FwdParams {
   float* out_loss;   // [1]
   float* out_terms;  // [4] var, dist, reg, qreg (unweighted)
   float* out_means;  // [bs][K][C]
+  const float* q_den;  // optional override of the q-regulariser denominator (data parallel), else null
   int G;             // CTAs per image (1 => CTA loops over images, no inter-CTA barrier)
   int strips, rowsplits, rpt;
 };
@@ -405,7 +406,8 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
       const float inv_bs = 1.f / (float)prm.bs;
       const double qs = __ldcg(prm.ws.qsum), nf = __ldcg(prm.ws.nfg);
       // discriminative.py:153-159: num = int(sum(target)); loss = sum(...)/num
-      const float qreg = (float)(qs / (double)(long long)nf);
+      const double qden = prm.q_den ? (double)__ldg(prm.q_den) : (double)(long long)nf;
+      const float qreg = (float)(qs / qden);
       const float var_t = v * inv_bs;
       const float dist_t = (prm.w_dist != 0.f) ? d * inv_bs : 0.f;
       const float reg_t = (prm.w_reg != 0.f) ? r * inv_bs : 0.f;
@@ -435,6 +437,7 @@ struct BwdParams {
   const float* means;       // [bs][K][C] forward output
   const float* grad_loss;   // [1] device scalar
   const float* grad_means;  // [bs][K][C] or null
+  const float* q_den;       // see FwdParams
   float* grad_emb;          // [bs][C][P]
 };
 
@@ -508,7 +511,8 @@ __global__ void __launch_bounds__(128) disc_bwd_prep_kernel(const BwdParams prm)
     prm.ws.coef[b] = cdir;
     if (b == 0) {
       const double nf = *prm.ws.nfg;
-      prm.ws.coef[prm.bs] = (float)((double)(go * prm.w_q) / (double)(long long)nf);
+      const double qden = prm.q_den ? (double)__ldg(prm.q_den) : (double)(long long)nf;
+      prm.ws.coef[prm.bs] = (float)((double)(go * prm.w_q) / qden);
     }
   }
 }
@@ -666,7 +670,7 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
                       int bs, int C, int H, int W, int K,
                       float delta_v, float delta_d, int norm, int normalize_means,
                       float w_var, float w_dist, float w_reg, float w_q,
-                      float* out_loss, float* out_terms, float* out_means,
+                      const float* q_den, float* out_loss, float* out_terms, float* out_means,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   int rc = check_common(target_kind, bs, C, H, W, K, norm);
   if (rc) return rc;
@@ -684,7 +688,7 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
   prm.bs = bs; prm.C = C; prm.H = H; prm.W = W; prm.K = K;
   prm.delta_v = delta_v; prm.delta_d = delta_d; prm.norm = norm; prm.normalize_means = normalize_means;
   prm.w_var = w_var; prm.w_dist = w_dist; prm.w_reg = w_reg; prm.w_q = w_q;
-  prm.out_loss = out_loss; prm.out_terms = out_terms; prm.out_means = out_means;
+  prm.out_loss = out_loss; prm.out_terms = out_terms; prm.out_means = out_means; prm.q_den = q_den;
 
   const int CP = pick_cp(C);
   const size_t smem = sizeof(float) * (size_t)K * (CP + 1);
@@ -722,7 +726,7 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
                       int bs, int C, int H, int W, int K,
                       float delta_v, float delta_d, int norm, int normalize_means,
                       float w_var, float w_dist, float w_reg, float w_q,
-                      const float* means, const float* grad_loss, const float* grad_means,
+                      const float* q_den, const float* means, const float* grad_loss, const float* grad_means,
                       float* grad_emb, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   int rc = check_common(target_kind, bs, C, H, W, K, norm);
   if (rc) return rc;
@@ -740,7 +744,7 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
   prm.bs = bs; prm.C = C; prm.H = H; prm.W = W; prm.K = K;
   prm.delta_v = delta_v; prm.delta_d = delta_d; prm.norm = norm; prm.normalize_means = normalize_means;
   prm.w_var = w_var; prm.w_dist = w_dist; prm.w_reg = w_reg; prm.w_q = w_q;
-  prm.means = means; prm.grad_loss = grad_loss; prm.grad_means = grad_means; prm.grad_emb = grad_emb;
+  prm.means = means; prm.grad_loss = grad_loss; prm.grad_means = grad_means; prm.grad_emb = grad_emb; prm.q_den = q_den;
 
   disc_bwd_prep_kernel<<<bs, 128, sizeof(float) * (size_t)K * C, stream>>>(prm);
   ISA_CUDA(cudaGetLastError());

@@ -11,6 +11,8 @@ target (bs, K, H, W) float / int64 / uint8 one-hot (or soft) masks as the refere
        collate emits them (dataset.py:354-376), or -- extension -- a uint8 label map
        (bs, H, W) with 255 = background (1 byte per pixel instead of 4K..8K)
 n_objects (bs,) ints;  max_n_objects == K.
+`q_denominator` (optional 1-element float CUDA tensor) overrides int(sum(target)) in the q-regulariser
+(discriminative.py:153-159) -- data parallel passes global_foreground / world_size.
 
 The shipped composite is  1.0 * variance + 0.005 * q_regulariser  with L2-normalised
 means (discriminative.py:168-186).  `terms=` switches the distance / regulariser terms
@@ -46,7 +48,7 @@ def _target_kind(target, input):
 class _DiscLossFn(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, input, target, n_objects, K, delta_v, delta_d, norm, normalize, terms):
+    def forward(ctx, input, target, n_objects, K, delta_v, delta_d, norm, normalize, terms, q_den=None):
         lib = _lib.load()
         _lib.require_cuda(input, "input")
         _lib.require_cuda(target, "target")
@@ -69,10 +71,10 @@ class _DiscLossFn(torch.autograd.Function):
         rc = lib.isa_disc_loss_fwd(
             _lib.ptr(x), _lib.ptr(tgt), kind, _lib.ptr(nobj), bs, C, H, W, K,
             delta_v, delta_d, norm, int(normalize), terms[0], terms[1], terms[2], terms[3],
-            loss.data_ptr(), terms_out.data_ptr(), _lib.ptr(means),
+            _lib.ptr(q_den), loss.data_ptr(), terms_out.data_ptr(), _lib.ptr(means),
             _lib.ptr(ws), ws_bytes, _lib.stream_ptr(x.device))
         _lib.check(rc, "isa_disc_loss_fwd")
-        ctx.save_for_backward(x, tgt, nobj, means, ws)
+        ctx.save_for_backward(x, tgt, nobj, means, ws, q_den)
         ctx.cfg = (kind, bs, C, H, W, K, delta_v, delta_d, norm, int(normalize), terms)
         ctx.mark_non_differentiable(terms_out)
         return loss, means, terms_out
@@ -80,7 +82,7 @@ class _DiscLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, grad_means, _grad_terms):
         lib = _lib.load()
-        x, tgt, nobj, means, ws = ctx.saved_tensors
+        x, tgt, nobj, means, ws, q_den = ctx.saved_tensors
         kind, bs, C, H, W, K, delta_v, delta_d, norm, normalize, terms = ctx.cfg
         if grad_loss is None:
             grad_loss = torch.zeros((), device=x.device, dtype=torch.float32)
@@ -92,10 +94,10 @@ class _DiscLossFn(torch.autograd.Function):
         rc = lib.isa_disc_loss_bwd(
             _lib.ptr(x), _lib.ptr(tgt), kind, _lib.ptr(nobj), bs, C, H, W, K,
             delta_v, delta_d, norm, normalize, terms[0], terms[1], terms[2], terms[3],
-            _lib.ptr(means), _lib.ptr(gl), _lib.ptr(gm), _lib.ptr(grad),
+            _lib.ptr(q_den), _lib.ptr(means), _lib.ptr(gl), _lib.ptr(gm), _lib.ptr(grad),
             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x.device))
         _lib.check(rc, "isa_disc_loss_bwd")
-        return grad, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None
 
 
 class DiscriminativeLoss(_Loss):
@@ -118,13 +120,13 @@ class DiscriminativeLoss(_Loss):
             raise _lib.IsaError("DiscriminativeLoss(usegpu=False): this build has no CPU path "
                                 "(the CPU restatement lives in oracle/ and is test-only)")
 
-    def forward(self, input, target, n_objects, max_n_objects):
+    def forward(self, input, target, n_objects, max_n_objects, q_denominator=None):
         K = int(max_n_objects)
         if target.dim() == 4 and target.size(1) != K:
             raise ValueError("target has %d instance channels but max_n_objects=%d "
                              "(the reference broadcast fails on this too)" % (target.size(1), K))
         loss, means, terms = _DiscLossFn.apply(input, target, n_objects, K, self.delta_var, self.delta_dist,
-                                               self.norm, self.normalize_means, self.terms)
+                                               self.norm, self.normalize_means, self.terms, q_denominator)
         self.last_terms = terms  # (var, dist, reg, qreg), unweighted, detached
         return loss, means
 

@@ -1,0 +1,246 @@
+"""`Model`: orchestration with the reference's API (/root/reference/code/lib/model.py:21-499):
+
+    Model(dataset, model_name, n_classes, max_n_objects, wae_opt=None, use_instance_segmentation=False,
+          use_wae=True, use_coords=False, load_model_path='', load_decoder_model_path='', usegpu=True)
+    .fit(criterion_type, delta_var, delta_dist, norm, learning_rate, weight_decay, clip_grad_norm,
+         lr_drop_factor, lr_drop_patience, optimize_bg, optimizer, train_cnn, n_epochs, class_weights,
+         train_loader, test_loader, model_save_path, debug)
+    .predict(images) -> (sem_probs (b,n_classes,h,w), embeddings (b,C,h,w), n_objects IntTensor (b,1))
+
+The reference file cannot be parsed by Python >= 3.7 (`cuda(async=True)`, model.py:221-225,476) and its
+training step takes `ins_cost` from a NaN-producing decoder; this is a rewrite with
+the same surface where the step is the designed one:
+    sem_logits, emb = net(True, images); ins_cost, means = criterion_discriminative(emb, ins, n, K)
+    cost = ins_cost + CE + Dice; backward; clip_grad_norm_; optimizer.step()
+Extras: `train_step(...)` (the public face of the reference's private __minibatch), device-resident
+`predict_device(...)`, and single-node data parallelism (`distributed=True`): one process per GPU,
+parameters replicated, ONE flat-bucket NCCL all-reduce of the gradients per step.
+visdom plotting and the pickle dumps to a hard-coded path (model.py:55,454-457) are dropped.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.optim as optim
+from torch.optim.lr_scheduler import ReduceLROnPlateau
+
+from . import _lib, parallel
+from .archs import ReSeg
+from .losses import DiscriminativeLoss
+from .seg_losses import DiceLoss
+
+
+class Model(object):
+
+    def __init__(self, dataset, model_name, n_classes, max_n_objects, wae_opt=None,
+                 use_instance_segmentation=False, use_wae=False, use_coords=False,
+                 load_model_path='', load_decoder_model_path='', usegpu=True,
+                 n_input=3, n_embedding=24, n_objects_prediction=16, distributed=False, device=None, net_kwargs=None):
+        self.dataset = dataset
+        self.model_name = model_name
+        self.n_classes = n_classes
+        self.max_n_objects = max_n_objects
+        self.use_instance_segmentation = use_instance_segmentation
+        self.use_coords = use_coords
+        self.load_model_path = load_model_path
+        self.load_decoder_model_path = load_decoder_model_path
+        self.use_wae = use_wae
+        self.usegpu = usegpu
+        self.n_objects_prediction = int(n_objects_prediction)
+        assert self.dataset in ['CVPPP', 'Cityscapes']
+        assert self.model_name in ['ReSeg']
+        if not usegpu:
+            raise _lib.IsaError("Model(usegpu=False): the hot path is sm_100a-only, there is no CPU fallback")
+        _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.model = ReSeg(self.n_classes, self.use_instance_segmentation, pretrained=False,
+                           use_coordinates=self.use_coords, use_wae=use_wae, usegpu=True,
+                           n_input=n_input, n_embedding=n_embedding, **(net_kwargs or {}))
+        self.__load_weights()
+        torch.backends.cudnn.benchmark = True          # model.py:50-52
+        self.model.to(self.device).to(memory_format=torch.channels_last)
+        self.distributed = bool(distributed) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:
+            self.__broadcast_parameters()
+        self._flat_grad = None
+        self.optimizer = None
+        self.lr_scheduler = None
+
+    # ------------------------------------------------------------------ weights
+    def __load_weights(self):
+        """Partial-load semantics of model.py:62-79: state_dict.update(pretrained)."""
+        if self.load_model_path != '':
+            assert os.path.isfile(self.load_model_path), 'Model : {} does not exists!'.format(self.load_model_path)
+            print('Loading model from {}'.format(self.load_model_path))
+            model_state_dict = self.model.state_dict()
+            pretrained_state_dict = torch.load(self.load_model_path, map_location='cpu')
+            model_state_dict.update(pretrained_state_dict)
+            self.model.load_state_dict(model_state_dict)
+
+    def __broadcast_parameters(self):
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            dist.broadcast(t.data, src=0)
+
+    # ------------------------------------------------------------------ criterion / optimizer
+    def define_criterion(self, class_weights, delta_var, delta_dist, norm=2, optimize_bg=False, criterion='CE'):
+        """model.py:99-139"""
+        assert criterion in ['CE', 'Dice', 'Multi', None]
+        smooth = 1.0
+        if self.use_instance_segmentation:
+            self.criterion_discriminative = DiscriminativeLoss(delta_var, delta_dist, norm, usegpu=True)
+        w = None
+        if class_weights is not None:
+            w = torch.as_tensor(class_weights, dtype=torch.float32, device=self.device)
+        if criterion in ['CE', 'Multi']:
+            self.criterion_ce = torch.nn.CrossEntropyLoss(w)
+        if criterion in ['Dice', 'Multi']:
+            self.criterion_dice = DiceLoss(optimize_bg=optimize_bg, weight=w, smooth=smooth)
+        self.criterion_type = criterion
+
+    def define_optimizer(self, learning_rate, weight_decay, lr_drop_factor, lr_drop_patience, optimizer='Adam'):
+        """model.py:141-160"""
+        assert optimizer in ['RMSprop', 'Adam', 'Adadelta', 'SGD']
+        parameters = [p for p in self.model.parameters() if p.requires_grad]
+        if optimizer == 'RMSprop':
+            self.optimizer = optim.RMSprop(parameters, lr=learning_rate, weight_decay=weight_decay)
+        elif optimizer == 'Adadelta':
+            self.optimizer = optim.Adadelta(parameters, lr=learning_rate, weight_decay=weight_decay)
+        elif optimizer == 'Adam':
+            self.optimizer = optim.Adam(parameters, lr=learning_rate, weight_decay=weight_decay)
+        else:
+            self.optimizer = optim.SGD(parameters, lr=learning_rate, momentum=0.9, weight_decay=weight_decay)
+        self.lr_scheduler = ReduceLROnPlateau(self.optimizer, mode='min', factor=lr_drop_factor, patience=lr_drop_patience)
+
+    # ------------------------------------------------------------------ data-parallel gradient exchange
+    def __allreduce_gradients(self):
+        """One flat fp32 bucket, one NCCL all-reduce (sum) over NVLink, then / world_size."""
+        if self._flat_grad is None:
+            self._flat_grad = parallel.FlatGradBucket(self.model.parameters())
+        self._flat_grad.allreduce(average=True)
+
+    def __q_denominator(self, ins):
+        """Global foreground count / world size (see parallel.py); None on a single process."""
+        if not self.distributed:
+            return None
+        if ins.dim() == 3:
+            local = (ins < self.max_n_objects).sum()
+        else:
+            local = ins.sum()
+        return parallel.global_q_denominator(local)
+
+    # ------------------------------------------------------------------ one step (model.py:162-281)
+    def train_step(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, clip_grad_norm=10.0,
+                   criterion_type=None, mode='training'):
+        """images (b,c,h,w) float; sem one-hot (b,n_classes,h,w); ins one-hot (b,K,h,w) (float/int64/uint8) or
+        a (b,h,w) uint8 label map; n_objects (b,).  CPU tensors are copied with non_blocking=True as the
+        reference does (.cuda(async=True)).  Returns the metrics dict of model.py:242-269 (device scalars)."""
+        criterion_type = criterion_type or self.criterion_type
+        training = mode == 'training'
+        self.model.train(training)
+        dev = self.device
+        images = images.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        sem = sem_seg_annotations.to(dev, non_blocking=True)
+        ins = ins_seg_annotations.to(dev, non_blocking=True)
+        nobj = torch.as_tensor(n_objects).to(dev, non_blocking=True).reshape(-1)
+        out_metrics = dict()
+        with torch.set_grad_enabled(training):
+            sem_seg_predictions, ins_seg_predictions = self.model(training, images)
+            cost = 0
+            if self.use_instance_segmentation:
+                ins_cost, _means = self.criterion_discriminative(ins_seg_predictions, ins, nobj, self.max_n_objects,
+                                                                 q_denominator=self.__q_denominator(ins))
+                cost = cost + ins_cost
+                out_metrics['INS Cost'] = ins_cost.detach()
+            if criterion_type in ['CE', 'Multi']:
+                _, sem_idx = sem.max(1)
+                ce_cost = self.criterion_ce(sem_seg_predictions, sem_idx)
+                cost = cost + ce_cost
+                out_metrics['CE Cost'] = ce_cost.detach()
+            if criterion_type in ['Dice', 'Multi']:
+                dice_cost = self.criterion_dice(sem_seg_predictions, sem, time=1)
+                cost = cost + dice_cost
+                out_metrics['Dice Cost'] = dice_cost.detach()
+            out_metrics['Cost'] = cost.detach()
+        if training:
+            if self._flat_grad is not None:
+                self._flat_grad.zero()
+            else:
+                self.model.zero_grad()
+            cost.backward()
+            if self.distributed:
+                self.__allreduce_gradients()
+            if clip_grad_norm != 0:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip_grad_norm)
+            self.optimizer.step()
+        return out_metrics
+
+    # ------------------------------------------------------------------ fit (model.py:358-464)
+    def fit(self, criterion_type, delta_var, delta_dist, norm, learning_rate, weight_decay, clip_grad_norm,
+            lr_drop_factor, lr_drop_patience, optimize_bg, optimizer, train_cnn, n_epochs, class_weights,
+            train_loader, test_loader, model_save_path, debug=False):
+        assert criterion_type in ['CE', 'Dice', 'Multi']
+        rank0 = (not self.distributed) or dist.get_rank() == 0
+        if rank0:
+            os.makedirs(model_save_path, exist_ok=True)
+            training_log_file = open(os.path.join(model_save_path, 'training.log'), 'w')
+            validation_log_file = open(os.path.join(model_save_path, 'validation.log'), 'w')
+            training_log_file.write('Epoch,Cost\n')
+            validation_log_file.write('Epoch,Cost\n')
+        self.define_criterion(class_weights, delta_var, delta_dist, norm=norm, optimize_bg=optimize_bg, criterion=criterion_type)
+        if not train_cnn:
+            for p in self.model.base.parameters():
+                p.requires_grad = False
+        self.define_optimizer(learning_rate, weight_decay, lr_drop_factor, lr_drop_patience, optimizer=optimizer)
+        best_val_cost = np.inf
+        history = []
+        for epoch in range(n_epochs):
+            t0 = time.time()
+            train_metrics = self.__run_epoch(train_loader, clip_grad_norm, 'training')
+            val_metrics = self.__run_epoch(test_loader, 0.0, 'test')
+            train_cost, val_cost = train_metrics['Cost'], val_metrics['Cost']
+            self.lr_scheduler.step(val_cost)
+            history.append((epoch, train_cost, val_cost))
+            if rank0:
+                print('Epoch : [{}/{}] - [{:.1f}s]  Training Cost {:.5f} | Validation Cost {:.5f}'.format(
+                    epoch, n_epochs, time.time() - t0, train_cost, val_cost))
+                if val_cost <= best_val_cost:
+                    best_val_cost = val_cost
+                    lr = self.optimizer.param_groups[0]['lr']
+                    torch.save(self.model.state_dict(), os.path.join(model_save_path, 'model_{}_{}_{}.pth'.format(epoch, val_cost, lr)))
+                training_log_file.write('{},{}\n'.format(epoch, train_cost))
+                validation_log_file.write('{},{}\n'.format(epoch, val_cost))
+                training_log_file.flush()
+                validation_log_file.flush()
+        if rank0:
+            training_log_file.close()
+            validation_log_file.close()
+        return history
+
+    def __run_epoch(self, loader, clip_grad_norm, mode):
+        sums, n = {}, 0
+        for images, sem, ins, nobj in loader:
+            m = self.train_step(images, sem, ins, nobj, clip_grad_norm, mode=mode)
+            for k, v in m.items():
+                sums[k] = sums.get(k, 0.0) + v
+            n += 1
+        return {k: float(v) / max(n, 1) for k, v in sums.items()}
+
+    # ------------------------------------------------------------------ predict (model.py:466-499)
+    @torch.no_grad()
+    def predict_device(self, images):
+        """-> (sem_probs, embeddings) on the device, nothing synchronised."""
+        assert len(images.size()) == 4  # b, c, h, w
+        self.model.eval()
+        images = images.to(self.device, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        sem_seg_predictions, ins_seg_predictions = self.model(False, images)
+        sem_seg_predictions = torch.nn.functional.softmax(sem_seg_predictions, dim=1)
+        return sem_seg_predictions, ins_seg_predictions
+
+    def predict(self, images):
+        sem, ins = self.predict_device(images)
+        if self.use_instance_segmentation:
+            n_objects_predictions = torch.IntTensor([[self.n_objects_prediction]] * images.size(0))
+            return sem.cpu(), ins.cpu(), n_objects_predictions
+        return sem.cpu()

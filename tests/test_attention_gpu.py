@@ -76,8 +76,17 @@ def test_mha_matches_reference_golden(cuda, golden_dir, case):
     m = min(Lq, Lk)
     np.testing.assert_allclose(attn[:, :m, :m].diagonal(dim1=1, dim2=2).cpu().numpy(), g[name + "_attn_diag"], atol=1e-5)
     assert _rel(tq.grad, torch.tensor(g[name + "_gq"])) < RTOL
+    bad = []
     for k_, p_ in mod.named_parameters():
-        assert _rel(p_.grad, torch.tensor(g[name + "_g_" + k_])) < 5e-4, k_
+        ref = torch.tensor(g[name + "_g_" + k_]).double()
+        # w_ks.bias has an exactly-zero gradient (softmax is shift invariant; the reference returns
+        # ~1e-6 of cancellation noise): scale by the matching weight gradient instead of by noise
+        wref = torch.tensor(g[name + "_g_" + k_.replace(".bias", ".weight")]).double()
+        scale = max(float(ref.abs().max()), float(wref.abs().max()))
+        err = float((p_.grad.double().cpu() - ref).abs().max())
+        if err >= 5e-4 * scale:
+            bad.append((k_, err, scale))
+    assert not bad, bad
 
 
 def test_fully_masked_row_is_nan_and_last_branch(cuda):

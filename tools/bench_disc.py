@@ -53,13 +53,13 @@ def main():
                                 ("dense_i64", 2, torch.tensor(synth.onehot(d["labels"], K, np.int64), device=dev), 8 * K)):
         def fwd():
             rc = lib.isa_disc_loss_fwd(x.data_ptr(), tgt.data_ptr(), code, n.data_ptr(), bs, C, H, W, K, 0.5, 1.5, 2, 1,
-                                       1.0, 0.0, 0.0, 0.005, loss.data_ptr(), terms.data_ptr(), means.data_ptr(),
+                                       1.0, 0.0, 0.0, 0.005, None, loss.data_ptr(), terms.data_ptr(), means.data_ptr(),
                                        ws.data_ptr(), wsb, st)
             assert rc == 0, lib.isa_last_error()
 
         def bwd():
             rc = lib.isa_disc_loss_bwd(x.data_ptr(), tgt.data_ptr(), code, n.data_ptr(), bs, C, H, W, K, 0.5, 1.5, 2, 1,
-                                       1.0, 0.0, 0.0, 0.005, means.data_ptr(), gl.data_ptr(), None, grad.data_ptr(),
+                                       1.0, 0.0, 0.0, 0.005, None, means.data_ptr(), gl.data_ptr(), None, grad.data_ptr(),
                                        ws.data_ptr(), wsb, st)
             assert rc == 0, lib.isa_last_error()
 

@@ -47,3 +47,11 @@ if what in ("renet",):
         y.backward(torch.ones_like(y))
     torch.cuda.synchronize()
     print("renet", float(y.sum()))
+if what in ("attn",):
+    from isa_b200.attention import scaled_dot_product_attention
+    torch.manual_seed(0)
+    q, k, v = [torch.randn(32, 4096, 12, device=dev, requires_grad=True) for _ in range(3)]
+    for _ in range(2):
+        o, _ = scaled_dot_product_attention(q, k, v, 12 ** 0.5)
+    torch.cuda.synchronize()
+    print("attn", float(o.sum()))
