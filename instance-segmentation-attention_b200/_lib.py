@@ -79,6 +79,66 @@ class IsaError(RuntimeError):
     pass
 
 
+# kernels launched per C-ABI call (memsets and copies not counted); used by bench.py's gpu_launches
+KERNELS_PER_CALL = {
+    "isa_disc_loss_fwd": 1, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1,
+    "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
+    "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 2,
+    "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1,
+}
+
+
+class CallTimer(object):
+    """Opt-in per-entry-point timing with CUDA events recorded on the launching stream (the stream the
+    kernels are enqueued on); used by bench.py for the roofline numbers.  Off by default: zero overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = {}   # name -> list of (start_event, end_event, meta)
+        self.counts = {}
+
+    def reset(self):
+        self.records = {}
+        self.counts = {}
+
+    def summary(self):
+        """-> {name: (n_calls, total_ms)}; synchronises."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in self.records.items():
+            out[name] = (len(evs), sum(s.elapsed_time(e) for s, e, _ in evs))
+        return out
+
+
+TIMER = CallTimer()
+
+
+class _TimedFn(object):
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+
+    def __call__(self, *args):
+        if not TIMER.enabled or self.name not in KERNELS_PER_CALL:
+            return self.fn(*args)
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.current_stream()
+        s.record(stream)
+        rc = self.fn(*args)
+        e.record(stream)
+        TIMER.records.setdefault(self.name, []).append((s, e, None))
+        TIMER.counts[self.name] = TIMER.counts.get(self.name, 0) + 1
+        return rc
+
+
+class _LibProxy(object):
+    def __init__(self, lib):
+        self._lib = lib
+        for name in SIGNATURES:
+            setattr(self, name, _TimedFn(name, getattr(lib, name)))
+
+
 def load():
     """Loads the shared library once; raises if it has not been built."""
     global _lib
@@ -96,7 +156,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        _lib = lib
+        _lib = _LibProxy(lib)
     return _lib
 
 

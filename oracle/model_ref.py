@@ -66,3 +66,52 @@ def discriminative_loss_torch(input, target, n_objects, max_n_objects, delta_v=0
     l2 = torch.norm(inp * t, 2, 2)
     reg_term = torch.sum(torch.pow(l2 - 1, 2)) / num
     return 1.0 * var_term + 0.005 * reg_term, means
+
+
+class _SkipVGG16Ref(nn.Module):
+    """Same layers / parameter names as isa_b200.archs.SkipVGG16 (stock convolutions, CPU)."""
+
+    def __init__(self, n_input=3):
+        super().__init__()
+
+        def block(cin, cout, n):
+            layers = []
+            for i in range(n):
+                layers += [nn.Conv2d(cin if i == 0 else cout, cout, 3, padding=1), nn.ReLU(inplace=True)]
+            return nn.Sequential(*layers)
+
+        self.stage1 = block(n_input, 64, 2)
+        self.stage2 = block(64, 128, 2)
+        self.stage3 = block(128, 256, 3)
+        self.pool = nn.MaxPool2d(2, 2)
+
+    def forward(self, x):
+        s1 = self.stage1(x)
+        s2 = self.stage2(self.pool(s1))
+        return self.stage3(self.pool(s2)), s1, s2
+
+
+class ReSegRef(nn.Module):
+    """isa_b200.archs.ReSeg with the hot path swapped for reference ops; state_dict keys are identical,
+    so weights interchange in both directions."""
+
+    def __init__(self, n_classes, n_input=3, n_embedding=24, n_units=100, n_head=2, d_k=12, d_v=12):
+        super().__init__()
+        self.base = _SkipVGG16Ref(n_input)
+        self.path = EmbeddingPathRef(256, n_units, n_head, n_embedding, d_k, d_v)
+        c = 2 * n_units + n_embedding
+        self.upsampling1 = nn.ConvTranspose2d(c, 100, kernel_size=(2, 2), stride=(2, 2))
+        self.relu1 = nn.ReLU()
+        self.upsampling2 = nn.ConvTranspose2d(100 + 128, 50, kernel_size=(2, 2), stride=(2, 2))
+        self.relu2 = nn.ReLU()
+        self.sem_seg_output = nn.Conv2d(50 + 64, n_classes, kernel_size=(1, 1), stride=(1, 1))
+        self.ins_seg_output = nn.Conv2d(50 + 64, n_embedding, kernel_size=(1, 1), stride=(1, 1))
+
+    def forward(self, training, x):
+        feats, s1, s2 = self.base(x)
+        y = self.path(feats)
+        y = self.relu1(self.upsampling1(y))
+        y = torch.cat((y, s2), dim=1)
+        y = self.relu2(self.upsampling2(y))
+        y = torch.cat((y, s1), dim=1)
+        return self.sem_seg_output(y), self.ins_seg_output(y)

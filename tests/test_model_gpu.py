@@ -47,8 +47,10 @@ def test_embedding_path_matches_reference_composition(cuda):
     assert _rel(yg, yr) < 5e-4
     yg.backward(gy.float().to(cuda))
     assert _rel(xg.grad, xr.grad) < 5e-4
+    gmax = max(float(q.grad.abs().max()) for q in ref.parameters())
     for (name, p), (_, q) in zip(mod.named_parameters(), ref.named_parameters()):
-        scale = max(float(q.grad.abs().max()), 1e-3 * float(xr.grad.abs().max()))
+        # w_ks.bias has an exactly-zero gradient (softmax shift invariance): floor the scale
+        scale = max(float(q.grad.abs().max()), 1e-2 * gmax)
         assert float((p.grad.double().cpu() - q.grad).abs().max()) < 1e-3 * scale, name
 
 
