@@ -22,7 +22,9 @@
 //   warps 2..5    one query row per thread: tcgen05.ld of S, online softmax in the exp2 domain,
 //                 P (bf16 hi/lo) -> shared memory as the next A operand, O rescale in TMEM,
 //                 epilogue O / l and the log-sum-exp for backward
-// Backward: recompute-based kernel on the CUDA cores (fp32) -- dQ, dK, dV from (q,k,v,dO,lse).
+// Backward: two more tcgen05 kernels with the same structure, recomputing P from the saved
+// log-sum-exp:  attn_bwd_dq (rows = queries:  S, dP -> dA = P (dP - delta) -> dQ += dA K) and
+// attn_bwd_dkdv (rows = keys: S^T, dP^T -> P^T, dA^T -> dV += P^T dO, dK += dA^T Q); no atomics.
 #include "isa_common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
@@ -39,6 +41,8 @@ constexpr int kQTileBytes = 2 * kOperandBytes;      // Qh | Ql
 constexpr int kPBytes = kTileQ * kTileK * 2;        // 32768: one bf16 [128][128] operand
 constexpr int kFwdThreads = 192;
 constexpr int kTmemCols = 256;                      // S: [0,128), O: [128,144)
+constexpr int kBwdThreads = 320;                    // warp 0 producer, warp 1 MMA, warps 2..9 math
+constexpr int kBwdTmemCols = 512;
 constexpr int kTmemO = 128;
 
 // canonical K-major no-swizzle layouts (units: bytes).  Element (row r, k):
@@ -152,8 +156,58 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// ---------------------------------------------------------------------------- prep
-// q [BH][Lq][d], k [BH][Lk][d], v [BH][Lk][dv] fp32  ->  tile-blocked bf16 hi/lo operands
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two fp32 -> packed bf16 hi parts and packed bf16 lo parts (x = hi + lo to ~16 mantissa bits)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);      // .x = a (low half), .y = b (high half)
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// 8 consecutive fp32 values -> one 16-byte group of the hi operand and one of the lo operand
+__device__ __forceinline__ void store_group(unsigned char* hi_base, unsigned char* lo_base, int off, const float (&x)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(x[2 * e], x[2 * e + 1], h[e], l[e]);
+  *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---------------------------------------------------------------------------- operand tile writers (prep)
+// [128 rows][16 k] K-major operand from src[row][c] (row stride ld, c < width), rows >= n_rows and c >= width zero.
+// 256 threads: thread -> (row r = tid/2, k group kg = tid%2)
+__device__ __forceinline__ void write_row_tile(unsigned char* dst_hi, unsigned char* dst_lo, const float* __restrict__ src, int ld, int width,
+                                               int row0, int n_rows, float scale) {
+  const int r = threadIdx.x >> 1, kg = threadIdx.x & 1;
+  const int row = row0 + r;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = kg * 8 + e;
+    x[e] = (row < n_rows && c < width) ? __ldg(src + (size_t)row * ld + c) * scale : 0.f;
+  }
+  store_group(dst_hi, dst_lo, kmajor_off(r, kg * 8, kSboQK), x);
+}
+// [16 rows = channel][128 k = position] K-major operand (the transpose), 256 threads: thread -> (n = tid/16, k group = tid%16)
+__device__ __forceinline__ void write_col_tile(unsigned char* dst_hi, unsigned char* dst_lo, const float* __restrict__ src, int ld, int width,
+                                               int row0, int n_rows, float scale) {
+  const int n = threadIdx.x >> 4, kgv = threadIdx.x & 15;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int row = row0 + kgv * 8 + e;
+    x[e] = (row < n_rows && n < width) ? __ldg(src + (size_t)row * ld + n) * scale : 0.f;
+  }
+  store_group(dst_hi, dst_lo, kmajor_off(n, kgv * 8, kSboP), x);
+}
+
 struct PrepParams {
   const float* q; const float* k; const float* v;
   unsigned char* qblk;   // [BH][nQt][Qh 4K | Ql 4K]
@@ -162,79 +216,62 @@ struct PrepParams {
   float qscale;          // log2(e) / temperature
 };
 
-__global__ void attn_prep_kernel(const PrepParams p) {
-  const int bh = blockIdx.y;
-  const int tile = blockIdx.x;
-  // one thread per (row, 8-element k group): 128 rows x 2 groups = 256 threads
-  const int r = threadIdx.x >> 1, kg = threadIdx.x & 1;
+__global__ void __launch_bounds__(256) attn_prep_kernel(const PrepParams p) {
+  const int bh = blockIdx.y, tile = blockIdx.x;
   if (tile < p.nQt) {
     unsigned char* dst = p.qblk + ((size_t)bh * p.nQt + tile) * kQTileBytes;
-    const int row = tile * kTileQ + r;
-    uint32_t hi4[4], lo4[4];
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      float x0 = 0.f, x1 = 0.f;
-      const int c0 = kg * 8 + e;
-      if (row < p.Lq) {
-        if (c0 < p.d) x0 = p.q[((size_t)bh * p.Lq + row) * p.d + c0] * p.qscale;
-        if (c0 + 1 < p.d) x1 = p.q[((size_t)bh * p.Lq + row) * p.d + c0 + 1] * p.qscale;
-      }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(x0, h0, l0); split_bf16(x1, h1, l1);
-      hi4[e >> 1] = pack2(h0, h1); lo4[e >> 1] = pack2(l0, l1);
-    }
-    const int off = kmajor_off(r, kg * 8, kSboQK);
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-    *reinterpret_cast<uint4*>(dst + kOperandBytes + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+    write_row_tile(dst, dst + kOperandBytes, p.q + (size_t)bh * p.Lq * p.d, p.d, p.d, tile * kTileQ, p.Lq, p.qscale);
   }
   if (tile < p.nKt) {
     unsigned char* dst = p.kvblk + ((size_t)bh * p.nKt + tile) * kKvTileBytes;
-    const int row = tile * kTileK + r;
-    uint32_t hi4[4], lo4[4];
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      float x0 = 0.f, x1 = 0.f;
-      const int c0 = kg * 8 + e;
-      if (row < p.Lk) {
-        if (c0 < p.d) x0 = p.k[((size_t)bh * p.Lk + row) * p.d + c0];
-        if (c0 + 1 < p.d) x1 = p.k[((size_t)bh * p.Lk + row) * p.d + c0 + 1];
-      }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(x0, h0, l0); split_bf16(x1, h1, l1);
-      hi4[e >> 1] = pack2(h0, h1); lo4[e >> 1] = pack2(l0, l1);
-    }
-    const int off = kmajor_off(r, kg * 8, kSboQK);
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-    *reinterpret_cast<uint4*>(dst + kOperandBytes + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
-    // V^T: operand rows = value channel n (16), k = key within the tile (128).
-    // thread -> (n = threadIdx.x / 16, key group kgv = threadIdx.x % 16): 8 consecutive keys
-    const int n = threadIdx.x >> 4, kgv = threadIdx.x & 15;
-    uint32_t vh[4], vl[4];
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      float x0 = 0.f, x1 = 0.f;
-      const int key0 = tile * kTileK + kgv * 8 + e;
-      if (n < p.dv) {
-        if (key0 < p.Lk) x0 = p.v[((size_t)bh * p.Lk + key0) * p.dv + n];
-        if (key0 + 1 < p.Lk) x1 = p.v[((size_t)bh * p.Lk + key0 + 1) * p.dv + n];
-      }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(x0, h0, l0); split_bf16(x1, h1, l1);
-      vh[e >> 1] = pack2(h0, h1); vl[e >> 1] = pack2(l0, l1);
-    }
-    const int offv = kmajor_off(n, kgv * 8, kSboP);
-    *reinterpret_cast<uint4*>(dst + 2 * kOperandBytes + offv) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-    *reinterpret_cast<uint4*>(dst + 3 * kOperandBytes + offv) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+    write_row_tile(dst, dst + kOperandBytes, p.k + (size_t)bh * p.Lk * p.d, p.d, p.d, tile * kTileK, p.Lk, 1.f);
+    write_col_tile(dst + 2 * kOperandBytes, dst + 3 * kOperandBytes, p.v + (size_t)bh * p.Lk * p.dv, p.dv, p.dv, tile * kTileK, p.Lk, 1.f);
   }
+}
+
+// ---------------------------------------------------------------------------- masks
+struct MaskArgs {
+  const unsigned char* key_mask;   // [n_mask_rows][Lk] 1 = masked, or null
+  const unsigned char* full_mask;  // [n_mask_rows][Lq][Lk] or null
+  int n_mask_rows;
+};
+// 128-bit mask of the keys [key0, key0+128) that are masked for query `row` (bit set = masked), incl. keys >= Lk
+__device__ __forceinline__ void key_bits(const MaskArgs& m, int bh, int row, int Lq, int Lk, int key0, uint32_t (&bits)[4]) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint32_t b = 0;
+    const int kb = key0 + w * 32;
+    if (kb + 32 > Lk) b = (kb >= Lk) ? 0xffffffffu : (0xffffffffu << (Lk - kb));
+    bits[w] = b;
+  }
+  if (m.key_mask) {
+    const unsigned char* km = m.key_mask + (size_t)(bh % m.n_mask_rows) * Lk;
+    for (int i = 0; i < 128 && key0 + i < Lk; ++i)
+      if (km[key0 + i]) bits[i >> 5] |= 1u << (i & 31);
+  }
+  if (m.full_mask && row < Lq) {
+    const unsigned char* fm = m.full_mask + ((size_t)(bh % m.n_mask_rows) * Lq + row) * Lk;
+    for (int i = 0; i < 128 && key0 + i < Lk; ++i)
+      if (fm[key0 + i]) bits[i >> 5] |= 1u << (i & 31);
+  }
+}
+// does this key tile need per-element masking at all?  (warp-uniform answer)
+__device__ __forceinline__ bool tile_needs_mask(const MaskArgs& m, int bh, int Lk, int key0, int lane) {
+  if (m.full_mask) return true;
+  bool any = key0 + kTileK > Lk;
+  if (m.key_mask) {
+    const unsigned char* km = m.key_mask + (size_t)(bh % m.n_mask_rows) * Lk;
+    for (int i = lane; i < 128; i += 32)
+      if (key0 + i < Lk && km[key0 + i]) any = true;
+  }
+  return __any_sync(0xffffffffu, any);
 }
 
 // ---------------------------------------------------------------------------- forward
 struct FwdParams {
   const unsigned char* qblk;
   const unsigned char* kvblk;
-  const unsigned char* key_mask;   // [n_mask_rows][Lk] 1 = masked, or null (row = bh % n_mask_rows)
-  const unsigned char* full_mask;  // [n_mask_rows][Lq][Lk] or null
-  int n_mask_rows;
+  MaskArgs mask;
   float* out;    // [BH][Lq][dv]
   float* lse2;   // [BH][Lq]  log2-domain log-sum-exp of the scaled scores (for backward)
   int BH, Lq, Lk, dv, nQt, nKt;
@@ -249,6 +286,48 @@ struct FwdSmem {
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint32_t tmem_base;
 };
+
+template <bool MASKED>
+__device__ __forceinline__ float fwd_tile_max(uint32_t t_row, const uint32_t (&bits)[4]) {
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float s[32];
+    tmem_ld32(t_row + c * 32, s);
+    if (MASKED) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (!((bits[c] >> i) & 1u)) m = fmaxf(m, s[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(s[i], s[i + 1]));
+    }
+  }
+  return m;
+}
+template <bool MASKED>
+__device__ __forceinline__ float fwd_tile_exp(uint32_t t_row, const uint32_t (&bits)[4], float m_safe, unsigned char* p_hi, unsigned char* p_lo, int r) {
+  float l = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float s[32];
+    tmem_ld32(t_row + c * 32, s);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = g * 8 + e;
+        float p = ex2_approx(s[i] - m_safe);
+        if (MASKED && ((bits[c] >> i) & 1u)) p = 0.f;
+        pv[e] = p;
+        l += p;
+      }
+      store_group(p_hi, p_lo, kmajor_off(r, c * 32 + g * 8, kSboP), pv);
+    }
+  }
+  return l;
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -322,64 +401,22 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
     const int r = quarter * 32 + lane;            // row inside the tile
     const int row = qt * kTileQ + r;
     const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-    const unsigned char* kmask = prm.key_mask ? prm.key_mask + (size_t)(bh % prm.n_mask_rows) * prm.Lk : nullptr;
-    const unsigned char* fmask = (prm.full_mask && row < prm.Lq) ? prm.full_mask + ((size_t)(bh % prm.n_mask_rows) * prm.Lq + row) * prm.Lk : nullptr;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nKt; ++j) {
+      const int key0 = j * kTileK;
+      const bool masked = tile_needs_mask(prm.mask, bh, prm.Lk, key0, lane);   // warp-uniform
+      uint32_t bits[4] = {0u, 0u, 0u, 0u};
+      if (masked) key_bits(prm.mask, bh, row, prm.Lq, prm.Lk, key0, bits);
       mbar_wait(&sm.s_full, j & 1);
       tc_fence_after();
-      const int key0 = j * kTileK;
-      // pass A: row maximum of the (masked) scores
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float s[32];
-        tmem_ld32(t_row + c * 32, s);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = key0 + c * 32 + i;
-          bool masked = key >= prm.Lk;
-          if (!masked && kmask) masked = kmask[key] != 0;
-          if (!masked && fmask) masked = fmask[key] != 0;
-          if (!masked) m_tile = fmaxf(m_tile, s[i]);
-        }
-      }
+      const float m_tile = masked ? fwd_tile_max<true>(t_row, bits) : fwd_tile_max<false>(t_row, bits);
       const float m_new = fmaxf(m_run, m_tile);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-      // pass B: p = exp2(s - m), row sum, bf16 hi/lo -> smem (A operand of the PV MMA)
-      float l_tile = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float s[32];
-        tmem_ld32(t_row + c * 32, s);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hi4[4], lo4[4];
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float pv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int i = g * 8 + e + u;
-              const int key = key0 + c * 32 + i;
-              bool masked = key >= prm.Lk;
-              if (!masked && kmask) masked = kmask[key] != 0;
-              if (!masked && fmask) masked = fmask[key] != 0;
-              pv[u] = masked ? 0.f : exp2f(s[i] - m_safe);
-              l_tile += pv[u];
-            }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(pv[0], h0, l0); split_bf16(pv[1], h1, l1);
-            hi4[e >> 1] = pack2(h0, h1); lo4[e >> 1] = pack2(l0, l1);
-          }
-          const int off = kmajor_off(r, c * 32 + g * 8, kSboP);
-          *reinterpret_cast<uint4*>(sm.p_hi + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-          *reinterpret_cast<uint4*>(sm.p_lo + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
-        }
-      }
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
+      const float l_tile = masked ? fwd_tile_exp<true>(t_row, bits, m_safe, sm.p_hi, sm.p_lo, r)
+                                  : fwd_tile_exp<false>(t_row, bits, m_safe, sm.p_hi, sm.p_lo, r);
       l_run = l_run * alpha + l_tile;
-      // rescale the running output (previous PV MMAs are complete: s_full was committed after them)
+      // rescale the running output (previous PV MMAs are complete: s_full was committed after them).
       // tcgen05.ld/st are warp-collective (.sync.aligned): the branch must be warp-uniform
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         float o[16];
@@ -430,120 +467,341 @@ __global__ void attn_probs_kernel(const float* __restrict__ q, const float* __re
   }
 }
 
-// ---------------------------------------------------------------------------- backward (CUDA cores, fp32, recompute)
-// One CTA = 64 keys of one head; loops over all queries in chunks of 64 staged in shared memory.
-//   p_ij = exp2(s_ij - lse2_i);  dp_ij = dO_i . v_j;  ds_ij = p_ij (dp_ij - delta_i)
-//   dV_j += p_ij dO_i;  dK_j += ds_ij q_i / T;  dQ_i += ds_ij k_j / T  (atomic, fp32)
-constexpr int kBwdK = 64, kBwdQ = 64, kBwdThreads = 256;
+// ---------------------------------------------------------------------------- backward
+// Per query tile (33 KB):  Q'h | Q'l | Q'^T h | Q'^T l | dOh | dOl | dO^T h | dO^T l | lse2[128] | delta[128]
+// Per key tile   (24 KB):  Kh | Kl | Vh | Vl | K^T h | K^T l
+// Q' = q * log2(e)/T, so S = Q' K^T is in the exp2 domain and P = exp2(S - lse2).
+// With A = dL/d(q.k/T) = P (dP - delta):  dQ = A K / T,  dK = ln2 * A^T Q',  dV = P^T dO.
+constexpr int kBwdQTileBytes = 8 * kOperandBytes + 1024;
+constexpr int kBwdKTileBytes = 6 * kOperandBytes;
 
-struct BwdParams {
+struct BwdPrepParams {
   const float* q; const float* k; const float* v; const float* dout; const float* out; const float* lse2;
-  const unsigned char* key_mask; const unsigned char* full_mask; int n_mask_rows;
-  float* dq; float* dk; float* dv;
-  int BH, Lq, Lk, d, dv_dim;
-  float qscale;   // log2(e)/T
-  float inv_t;    // 1/T
+  unsigned char* qtiles; unsigned char* ktiles;
+  int BH, Lq, Lk, d, dv, nQt, nKt;
+  float qscale;
 };
 
-__global__ void attn_delta_kernel(const float* __restrict__ dout, const float* __restrict__ out, int rows, int dv, float* __restrict__ delta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows) return;
-  float s = 0.f;
-  for (int c = 0; c < dv; ++c) s = fmaf(dout[(size_t)i * dv + c], out[(size_t)i * dv + c], s);
-  delta[i] = s;
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const BwdPrepParams p) {
+  const int bh = blockIdx.y, tile = blockIdx.x;
+  if (tile < p.nQt) {
+    unsigned char* dst = p.qtiles + ((size_t)bh * p.nQt + tile) * kBwdQTileBytes;
+    const float* q = p.q + (size_t)bh * p.Lq * p.d;
+    const float* go = p.dout + (size_t)bh * p.Lq * p.dv;
+    write_row_tile(dst, dst + kOperandBytes, q, p.d, p.d, tile * kTileQ, p.Lq, p.qscale);
+    write_col_tile(dst + 2 * kOperandBytes, dst + 3 * kOperandBytes, q, p.d, p.d, tile * kTileQ, p.Lq, p.qscale);
+    write_row_tile(dst + 4 * kOperandBytes, dst + 5 * kOperandBytes, go, p.dv, p.dv, tile * kTileQ, p.Lq, 1.f);
+    write_col_tile(dst + 6 * kOperandBytes, dst + 7 * kOperandBytes, go, p.dv, p.dv, tile * kTileQ, p.Lq, 1.f);
+    if (threadIdx.x < kTileQ) {
+      const int row = tile * kTileQ + threadIdx.x;
+      float l2 = 0.f, dl = 0.f;
+      if (row < p.Lq) {
+        l2 = p.lse2[(size_t)bh * p.Lq + row];
+        const float* o = p.out + ((size_t)bh * p.Lq + row) * p.dv;
+        for (int c = 0; c < p.dv; ++c) dl = fmaf(go[(size_t)row * p.dv + c], o[c], dl);
+      }
+      float* st = reinterpret_cast<float*>(dst + 8 * kOperandBytes);
+      st[threadIdx.x] = l2;
+      st[kTileQ + threadIdx.x] = dl;
+    }
+  }
+  if (tile < p.nKt) {
+    unsigned char* dst = p.ktiles + ((size_t)bh * p.nKt + tile) * kBwdKTileBytes;
+    const float* k = p.k + (size_t)bh * p.Lk * p.d;
+    const float* v = p.v + (size_t)bh * p.Lk * p.dv;
+    write_row_tile(dst, dst + kOperandBytes, k, p.d, p.d, tile * kTileK, p.Lk, 1.f);
+    write_row_tile(dst + 2 * kOperandBytes, dst + 3 * kOperandBytes, v, p.dv, p.dv, tile * kTileK, p.Lk, 1.f);
+    write_col_tile(dst + 4 * kOperandBytes, dst + 5 * kOperandBytes, k, p.d, p.d, tile * kTileK, p.Lk, 1.f);
+  }
 }
 
-__global__ void __launch_bounds__(kBwdThreads) attn_bwd_kernel(const BwdParams prm, const float* __restrict__ delta) {
-  __shared__ float s_k[kBwdK][kDP + 1], s_v[kBwdK][kDP + 1];
-  __shared__ float s_q[kBwdQ][kDP + 1], s_do[kBwdQ][kDP + 1];
-  __shared__ float s_l[kBwdQ], s_dl[kBwdQ];
-  __shared__ float s_dq[kBwdQ][kDP + 1];
-  const int bh = blockIdx.y, k0 = blockIdx.x * kBwdK;
-  const int d = prm.d, dvd = prm.dv_dim;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < kBwdK * kDP; idx += kBwdThreads) {
-    const int r = idx / kDP, c = idx % kDP;
-    const int key = k0 + r;
-    s_k[r][c] = (key < prm.Lk && c < d) ? prm.k[((size_t)bh * prm.Lk + key) * d + c] : 0.f;
-    s_v[r][c] = (key < prm.Lk && c < dvd) ? prm.v[((size_t)bh * prm.Lk + key) * dvd + c] : 0.f;
-  }
-  // thread -> key jj = tid % 64, query sub-lane qs = tid / 64 (4 query groups interleaved)
-  const int jj = tid % kBwdK, qs = tid / kBwdK;
-  const int key = k0 + jj;
-  float dk_acc[kDP], dv_acc[kDP];
-#pragma unroll
-  for (int c = 0; c < kDP; ++c) { dk_acc[c] = 0.f; dv_acc[c] = 0.f; }
-  const unsigned char* kmask = prm.key_mask ? prm.key_mask + (size_t)(bh % prm.n_mask_rows) * prm.Lk : nullptr;
-  const bool key_ok = key < prm.Lk && !(kmask && kmask[key] != 0);
-  __syncthreads();
-  float kreg[kDP], vreg[kDP];
-#pragma unroll
-  for (int c = 0; c < kDP; ++c) { kreg[c] = s_k[jj][c]; vreg[c] = s_v[jj][c]; }
+struct BwdParams {
+  const unsigned char* qtiles; const unsigned char* ktiles;
+  MaskArgs mask;
+  float* dq; float* dk; float* dv;
+  int BH, Lq, Lk, d, dv_dim, nQt, nKt;
+  float inv_t;
+};
 
-  for (int q0 = 0; q0 < prm.Lq; q0 += kBwdQ) {
-    __syncthreads();
-    for (int idx = tid; idx < kBwdQ * kDP; idx += kBwdThreads) {
-      const int r = idx / kDP, c = idx % kDP;
-      const int qi = q0 + r;
-      s_q[r][c] = (qi < prm.Lq && c < d) ? prm.q[((size_t)bh * prm.Lq + qi) * d + c] : 0.f;
-      s_do[r][c] = (qi < prm.Lq && c < dvd) ? prm.dout[((size_t)bh * prm.Lq + qi) * dvd + c] : 0.f;
-      s_dq[r][c] = 0.f;
+// TMEM columns of both backward kernels: S [0,128), dP [128,256), accumulators from 256
+constexpr int kTmS = 0, kTmDP = 128, kTmAcc0 = 256, kTmAcc1 = 272;
+
+struct DqSmem {
+  unsigned char q[2 * kOperandBytes];            // Q'h | Q'l
+  unsigned char go[2 * kOperandBytes];           // dOh | dOl
+  unsigned char kt[kStages][kBwdKTileBytes];     // Kh | Kl | Vh | Vl | K^T h | K^T l
+  unsigned char a_hi[kPBytes], a_lo[kPBytes];    // dA (A operand of dQ += dA K)
+  uint64_t c_full, s_full, a_full, o_full;
+  uint64_t kv_full[kStages], kv_empty[kStages];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const BwdParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DqSmem& sm = *reinterpret_cast<DqSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, bh = blockIdx.y;
+  const int nKt = prm.nKt;
+  const unsigned char* qtile = prm.qtiles + ((size_t)bh * prm.nQt + qt) * kBwdQTileBytes;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.c_full, 1); mbar_init(&sm.s_full, 1); mbar_init(&sm.a_full, 256); mbar_init(&sm.o_full, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.c_full, 4 * kOperandBytes);
+      tma_bulk_g2s(sm.q, qtile, 2 * kOperandBytes, &sm.c_full);
+      tma_bulk_g2s(sm.go, qtile + 4 * kOperandBytes, 2 * kOperandBytes, &sm.c_full);
+      for (int j = 0; j < nKt; ++j) {
+        const int st = j % kStages;
+        mbar_wait(&sm.kv_empty[st], ((j / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&sm.kv_full[st], kBwdKTileBytes);
+        tma_bulk_g2s(sm.kt[st], prm.ktiles + ((size_t)bh * nKt + j) * kBwdKTileBytes, kBwdKTileBytes, &sm.kv_full[st]);
+      }
     }
-    for (int r = tid; r < kBwdQ; r += kBwdThreads) {
-      const int qi = q0 + r;
-      s_l[r] = (qi < prm.Lq) ? prm.lse2[(size_t)bh * prm.Lq + qi] : 0.f;
-      s_dl[r] = (qi < prm.Lq) ? delta[(size_t)bh * prm.Lq + qi] : 0.f;
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, 128);
+      constexpr uint32_t idesc_o = make_idesc(128, kDP);
+      const uint32_t q_hi = smem_u32(sm.q), q_lo = q_hi + kOperandBytes;
+      const uint32_t g_hi = smem_u32(sm.go), g_lo = g_hi + kOperandBytes;
+      const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+      mbar_wait(&sm.c_full, 0);
+      for (int j = 0; j < nKt; ++j) {
+        const int st = j % kStages;
+        const uint32_t kb = smem_u32(sm.kt[st]);
+        const uint32_t k_hi = kb, k_lo = kb + kOperandBytes, v_hi = kb + 2 * kOperandBytes, v_lo = kb + 3 * kOperandBytes;
+        const uint32_t kt_hi = kb + 4 * kOperandBytes, kt_lo = kb + 5 * kOperandBytes;
+        mbar_wait(&sm.kv_full[st], (j / kStages) & 1);
+        tc_fence_after();
+        // S = Q' K^T ; dP = dO V^T
+        umma_bf16(tmem + kTmS, make_desc(q_hi, 128, kSboQK), make_desc(k_hi, 128, kSboQK), idesc_s, 0);
+        umma_bf16(tmem + kTmS, make_desc(q_hi, 128, kSboQK), make_desc(k_lo, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tmem + kTmS, make_desc(q_lo, 128, kSboQK), make_desc(k_hi, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tmem + kTmDP, make_desc(g_hi, 128, kSboQK), make_desc(v_hi, 128, kSboQK), idesc_s, 0);
+        umma_bf16(tmem + kTmDP, make_desc(g_hi, 128, kSboQK), make_desc(v_lo, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tmem + kTmDP, make_desc(g_lo, 128, kSboQK), make_desc(v_hi, 128, kSboQK), idesc_s, 1);
+        umma_commit(&sm.s_full);
+        mbar_wait(&sm.a_full, j & 1);
+        tc_fence_after();
+        // dQ += dA K   (B = K^T tile)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t ko = kk * 256;
+          umma_bf16(tmem + kTmAcc0, make_desc(a_hi + ko, 128, kSboP), make_desc(kt_hi + ko, 128, kSboP), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16(tmem + kTmAcc0, make_desc(a_hi + ko, 128, kSboP), make_desc(kt_lo + ko, 128, kSboP), idesc_o, 1);
+          umma_bf16(tmem + kTmAcc0, make_desc(a_lo + ko, 128, kSboP), make_desc(kt_hi + ko, 128, kSboP), idesc_o, 1);
+        }
+        umma_commit(&sm.kv_empty[st]);
+      }
+      umma_commit(&sm.o_full);
     }
-    __syncthreads();
-    for (int r = qs; r < kBwdQ; r += kBwdThreads / kBwdK) {
-      const int qi = q0 + r;
-      float ds = 0.f;
-      if (qi < prm.Lq && key_ok) {
-        bool masked = false;
-        if (prm.full_mask) masked = prm.full_mask[((size_t)(bh % prm.n_mask_rows) * prm.Lq + qi) * prm.Lk + key] != 0;
-        if (!masked) {
-          float s = 0.f, dp = 0.f;
+  } else {
+    // 8 math warps: (TMEM quarter = warp % 4, column half = (warp - 2) / 4)
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int row = qt * kTileQ + r;
+    const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
+    const float* stats = reinterpret_cast<const float*>(qtile + 8 * kOperandBytes);
+    const float l2 = __ldg(stats + r), dl = __ldg(stats + kTileQ + r);
+    for (int j = 0; j < nKt; ++j) {
+      const int key0 = j * kTileK;
+      const bool masked = tile_needs_mask(prm.mask, bh, prm.Lk, key0, lane);
+      uint32_t bits[4] = {0u, 0u, 0u, 0u};
+      if (masked) key_bits(prm.mask, bh, row, prm.Lq, prm.Lk, key0, bits);
+      mbar_wait(&sm.s_full, j & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        float s[32], dp[32];
+        tmem_ld32(t_row + kTmS + c * 32, s);
+        tmem_ld32(t_row + kTmDP + c * 32, dp);
 #pragma unroll
-          for (int c = 0; c < kDP; ++c) { s = fmaf(s_q[r][c], kreg[c], s); dp = fmaf(s_do[r][c], vreg[c], dp); }
-          const float p = exp2f(s * prm.qscale - s_l[r]);
-          ds = p * (dp - s_dl[r]) * prm.inv_t;
+        for (int g = 0; g < 4; ++g) {
+          float a[8];
 #pragma unroll
-          for (int c = 0; c < kDP; ++c) { dv_acc[c] = fmaf(p, s_do[r][c], dv_acc[c]); dk_acc[c] = fmaf(ds, s_q[r][c], dk_acc[c]); }
+          for (int e = 0; e < 8; ++e) {
+            const int i = g * 8 + e;
+            float p = ex2_approx(s[i] - l2);
+            if (masked && ((bits[c] >> i) & 1u)) p = 0.f;
+            a[e] = p * (dp[i] - dl);
+          }
+          store_group(sm.a_hi, sm.a_lo, kmajor_off(r, c * 32 + g * 8, kSboP), a);
         }
       }
-      // dQ_i += sum_j ds_ij k_j : reduce over the 64 keys of this CTA (two warps per query row)
-#pragma unroll
-      for (int c = 0; c < kDP; ++c) {
-        float t = ds * kreg[c];
-        t = warp_sum(t);
-        if ((tid & 31) == 0 && c < d) atomicAdd(&s_dq[r][c], t);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&sm.a_full);
+    }
+    mbar_wait(&sm.o_full, 0);
+    tc_fence_after();
+    if (half == 0) {
+      float o[16];
+      tmem_ld16(t_row + kTmAcc0, o);
+      if (row < prm.Lq) {
+        float* dst = prm.dq + ((size_t)bh * prm.Lq + row) * prm.d;
+        for (int i = 0; i < prm.d; ++i) dst[i] = o[i] * prm.inv_t;
       }
     }
-    __syncthreads();
-    for (int idx = tid; idx < kBwdQ * d; idx += kBwdThreads) {
-      const int r = idx / d, c = idx % d;
-      const int qi = q0 + r;
-      if (qi < prm.Lq) atomicAdd(prm.dq + ((size_t)bh * prm.Lq + qi) * d + c, s_dq[r][c]);
-    }
   }
-  // combine the 4 query groups of each key
+  tc_fence_before();
   __syncthreads();
-  float(*s_red)[kDP + 1] = s_q;  // reuse [64][17]
-  for (int pass = 0; pass < 2; ++pass) {
-    float* acc = pass == 0 ? dk_acc : dv_acc;
-    for (int g = 1; g < kBwdThreads / kBwdK; ++g) {
-      __syncthreads();
-      if (qs == g)
-        for (int c = 0; c < kDP; ++c) s_red[jj][c] = acc[c];
-      __syncthreads();
-      if (qs == 0)
-        for (int c = 0; c < kDP; ++c) acc[c] += s_red[jj][c];
+  if (warp == 1) tmem_dealloc(tmem, kBwdTmemCols);
+}
+
+struct DkvSmem {
+  unsigned char kv[4 * kOperandBytes];                       // Kh | Kl | Vh | Vl   (this CTA's key tile)
+  unsigned char qt[kStages][kBwdQTileBytes];                 // per query tile (33 KB)
+  unsigned char p_hi[kPBytes], p_lo[kPBytes];                // P^T
+  unsigned char a_hi[kPBytes], a_lo[kPBytes];                // dA^T
+  uint64_t c_full, s_full, a_full, o_full;
+  uint64_t q_full[kStages], q_empty[kStages];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const BwdParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DkvSmem& sm = *reinterpret_cast<DkvSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, bh = blockIdx.y;
+  const int nQt = prm.nQt;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.c_full, 1); mbar_init(&sm.s_full, 1); mbar_init(&sm.a_full, 256); mbar_init(&sm.o_full, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.c_full, 4 * kOperandBytes);
+      tma_bulk_g2s(sm.kv, prm.ktiles + ((size_t)bh * prm.nKt + kt) * kBwdKTileBytes, 4 * kOperandBytes, &sm.c_full);
+      for (int i = 0; i < nQt; ++i) {
+        const int st = i % kStages;
+        mbar_wait(&sm.q_empty[st], ((i / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&sm.q_full[st], kBwdQTileBytes);
+        tma_bulk_g2s(sm.qt[st], prm.qtiles + ((size_t)bh * nQt + i) * kBwdQTileBytes, kBwdQTileBytes, &sm.q_full[st]);
+      }
     }
-    if (qs == 0 && key < prm.Lk) {
-      if (pass == 0) for (int c = 0; c < d; ++c) prm.dk[((size_t)bh * prm.Lk + key) * d + c] = acc[c];
-      else for (int c = 0; c < dvd; ++c) prm.dv[((size_t)bh * prm.Lk + key) * dvd + c] = acc[c];
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, 128);
+      constexpr uint32_t idesc_o = make_idesc(128, kDP);
+      const uint32_t k_hi = smem_u32(sm.kv), k_lo = k_hi + kOperandBytes, v_hi = k_hi + 2 * kOperandBytes, v_lo = k_hi + 3 * kOperandBytes;
+      const uint32_t p_hi = smem_u32(sm.p_hi), p_lo = smem_u32(sm.p_lo), a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+      mbar_wait(&sm.c_full, 0);
+      for (int i = 0; i < nQt; ++i) {
+        const int st = i % kStages;
+        const uint32_t qb = smem_u32(sm.qt[st]);
+        const uint32_t q_hi = qb, q_lo = qb + kOperandBytes, qT_hi = qb + 2 * kOperandBytes, qT_lo = qb + 3 * kOperandBytes;
+        const uint32_t g_hi = qb + 4 * kOperandBytes, g_lo = qb + 5 * kOperandBytes, gT_hi = qb + 6 * kOperandBytes, gT_lo = qb + 7 * kOperandBytes;
+        mbar_wait(&sm.q_full[st], (i / kStages) & 1);
+        tc_fence_after();
+        // S^T = K Q'^T ; dP^T = V dO^T   (rows = keys, columns = queries)
+        umma_bf16(tmem + kTmS, make_desc(k_hi, 128, kSboQK), make_desc(q_hi, 128, kSboQK), idesc_s, 0);
+        umma_bf16(tmem + kTmS, make_desc(k_hi, 128, kSboQK), make_desc(q_lo, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tmem + kTmS, make_desc(k_lo, 128, kSboQK), make_desc(q_hi, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tmem + kTmDP, make_desc(v_hi, 128, kSboQK), make_desc(g_hi, 128, kSboQK), idesc_s, 0);
+        umma_bf16(tmem + kTmDP, make_desc(v_hi, 128, kSboQK), make_desc(g_lo, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tmem + kTmDP, make_desc(v_lo, 128, kSboQK), make_desc(g_hi, 128, kSboQK), idesc_s, 1);
+        umma_commit(&sm.s_full);
+        mbar_wait(&sm.a_full, i & 1);
+        tc_fence_after();
+        // dV += P^T dO (B = dO^T tile) ; dK += dA^T Q' (B = Q'^T tile)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t ko = kk * 256;
+          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem + kTmAcc0, make_desc(p_hi + ko, 128, kSboP), make_desc(gT_hi + ko, 128, kSboP), idesc_o, acc);
+          umma_bf16(tmem + kTmAcc0, make_desc(p_hi + ko, 128, kSboP), make_desc(gT_lo + ko, 128, kSboP), idesc_o, 1);
+          umma_bf16(tmem + kTmAcc0, make_desc(p_lo + ko, 128, kSboP), make_desc(gT_hi + ko, 128, kSboP), idesc_o, 1);
+          umma_bf16(tmem + kTmAcc1, make_desc(a_hi + ko, 128, kSboP), make_desc(qT_hi + ko, 128, kSboP), idesc_o, acc);
+          umma_bf16(tmem + kTmAcc1, make_desc(a_hi + ko, 128, kSboP), make_desc(qT_lo + ko, 128, kSboP), idesc_o, 1);
+          umma_bf16(tmem + kTmAcc1, make_desc(a_lo + ko, 128, kSboP), make_desc(qT_hi + ko, 128, kSboP), idesc_o, 1);
+        }
+        umma_commit(&sm.q_empty[st]);
+      }
+      umma_commit(&sm.o_full);
+    }
+  } else {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;            // key row inside the tile
+    const int key = kt * kTileK + r;
+    const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
+    bool row_masked = key >= prm.Lk;
+    if (!row_masked && prm.mask.key_mask) row_masked = prm.mask.key_mask[(size_t)(bh % prm.mask.n_mask_rows) * prm.Lk + key] != 0;
+    const unsigned char* fm = prm.mask.full_mask ? prm.mask.full_mask + (size_t)(bh % prm.mask.n_mask_rows) * prm.Lq * prm.Lk : nullptr;
+    for (int i = 0; i < nQt; ++i) {
+      const int st = i % kStages;
+      const int q0 = i * kTileQ;
+      mbar_wait(&sm.q_full[st], (i / kStages) & 1);     // lse2 / delta of this query tile are in smem
+      const float* stats = reinterpret_cast<const float*>(sm.qt[st] + 8 * kOperandBytes);
+      mbar_wait(&sm.s_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        float s[32], dp[32];
+        tmem_ld32(t_row + kTmS + c * 32, s);
+        tmem_ld32(t_row + kTmDP + c * 32, dp);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float p8[8], a8[8];
+          const float4 l2a = *reinterpret_cast<const float4*>(stats + c * 32 + g * 8);
+          const float4 l2b = *reinterpret_cast<const float4*>(stats + c * 32 + g * 8 + 4);
+          const float4 dla = *reinterpret_cast<const float4*>(stats + kTileQ + c * 32 + g * 8);
+          const float4 dlb = *reinterpret_cast<const float4*>(stats + kTileQ + c * 32 + g * 8 + 4);
+          const float l2v[8] = {l2a.x, l2a.y, l2a.z, l2a.w, l2b.x, l2b.y, l2b.z, l2b.w};
+          const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ii = g * 8 + e;
+            const int qi = q0 + c * 32 + ii;
+            float p = ex2_approx(s[ii] - l2v[e]);
+            bool mk = row_masked || qi >= prm.Lq;
+            if (fm && !mk) mk = fm[(size_t)qi * prm.Lk + key] != 0;
+            if (mk) p = 0.f;
+            p8[e] = p;
+            a8[e] = p * (dp[ii] - dlv[e]);
+          }
+          const int off = kmajor_off(r, c * 32 + g * 8, kSboP);
+          store_group(sm.p_hi, sm.p_lo, off, p8);
+          store_group(sm.a_hi, sm.a_lo, off, a8);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&sm.a_full);
+    }
+    mbar_wait(&sm.o_full, 0);
+    tc_fence_after();
+    float o[16];
+    tmem_ld16(t_row + (half == 0 ? kTmAcc0 : kTmAcc1), o);
+    if (key < prm.Lk) {
+      if (half == 0) {
+        float* dst = prm.dv + ((size_t)bh * prm.Lk + key) * prm.dv_dim;
+        for (int c = 0; c < prm.dv_dim; ++c) dst[c] = o[c];
+      } else {
+        float* dst = prm.dk + ((size_t)bh * prm.Lk + key) * prm.d;
+        for (int c = 0; c < prm.d; ++c) dst[c] = o[c] * 0.6931471805599453f;   // ln 2: S was in the exp2 domain
+      }
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kBwdTmemCols);
 }
 
 int check_attn(int BH, int Lq, int Lk, int d, int dv) {
@@ -553,15 +811,23 @@ int check_attn(int BH, int Lq, int Lk, int d, int dv) {
   return ISA_OK;
 }
 
+size_t fwd_ws_bytes(int BH, int Lq, int Lk) {
+  const size_t nQt = (Lq + kTileQ - 1) / kTileQ, nKt = (Lk + kTileK - 1) / kTileK;
+  return isa_align_up((size_t)BH * nQt * kQTileBytes, 1024) + isa_align_up((size_t)BH * nKt * kKvTileBytes, 1024);
+}
+size_t bwd_ws_bytes(int BH, int Lq, int Lk) {
+  const size_t nQt = (Lq + kTileQ - 1) / kTileQ, nKt = (Lk + kTileK - 1) / kTileK;
+  return isa_align_up((size_t)BH * nQt * kBwdQTileBytes, 1024) + isa_align_up((size_t)BH * nKt * kBwdKTileBytes, 1024);
+}
+
 }  // namespace
 
 extern "C" {
 
 size_t isa_attention_workspace_bytes(int BH, int Lq, int Lk) {
   if (BH <= 0 || Lq <= 0 || Lk <= 0) return 0;
-  const size_t nQt = (Lq + kTileQ - 1) / kTileQ, nKt = (Lk + kTileK - 1) / kTileK;
-  return isa_align_up((size_t)BH * nQt * kQTileBytes, 1024) + isa_align_up((size_t)BH * nKt * kKvTileBytes, 1024) +
-         isa_align_up(sizeof(float) * (size_t)BH * Lq, 1024);
+  const size_t a = fwd_ws_bytes(BH, Lq, Lk), b = bwd_ws_bytes(BH, Lq, Lk);
+  return a > b ? a : b;
 }
 
 // q [BH][Lq][d], k [BH][Lk][d], v [BH][Lk][dv] fp32; temperature T (= sqrt(d_k) in the reference);
@@ -592,7 +858,8 @@ int isa_attention_fwd(const float* q, const float* k, const float* v, int BH, in
   attn_prep_kernel<<<dim3(nQt > nKt ? nQt : nKt, BH), 256, 0, stream>>>(pp);
   ISA_CUDA(cudaGetLastError());
   FwdParams fp;
-  fp.qblk = qblk; fp.kvblk = kvblk; fp.key_mask = key_mask; fp.full_mask = full_mask; fp.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
+  fp.qblk = qblk; fp.kvblk = kvblk;
+  fp.mask.key_mask = key_mask; fp.mask.full_mask = full_mask; fp.mask.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
   fp.out = out; fp.lse2 = lse2; fp.BH = BH; fp.Lq = Lq; fp.Lk = Lk; fp.dv = dv; fp.nQt = nQt; fp.nKt = nKt;
   const size_t smem = sizeof(FwdSmem) + 1024;
   ISA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -616,7 +883,7 @@ int isa_attention_probs(const float* q, const float* k, const float* lse2, int B
   return ISA_OK;
 }
 
-// dq/dk/dv from (q,k,v,out,dout,lse2); dq is zeroed here.  workspace: same size as forward (its tail holds delta).
+// dq/dk/dv from (q,k,v,out,dout,lse2); workspace: isa_attention_workspace_bytes (contents of forward are not needed).
 int isa_attention_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout, const float* lse2,
                       int BH, int Lq, int Lk, int d, int dv, float temperature,
                       const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
@@ -628,17 +895,25 @@ int isa_attention_bwd(const float* q, const float* k, const float* v, const floa
     isa_set_error("attention_bwd: workspace too small");
     return ISA_ERR_WORKSPACE;
   }
-  const size_t nQt = (Lq + kTileQ - 1) / kTileQ, nKt = (Lk + kTileK - 1) / kTileK;
-  float* delta = (float*)((unsigned char*)workspace + isa_align_up((size_t)BH * nQt * kQTileBytes, 1024) + isa_align_up((size_t)BH * nKt * kKvTileBytes, 1024));
-  const int rows = BH * Lq;
-  attn_delta_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(dout, out, rows, dv, delta);
-  ISA_CUDA(cudaMemsetAsync(dq, 0, sizeof(float) * (size_t)BH * Lq * d, stream));
+  const int nQt = (Lq + kTileQ - 1) / kTileQ, nKt = (Lk + kTileK - 1) / kTileK;
+  unsigned char* qtiles = (unsigned char*)workspace;
+  unsigned char* ktiles = qtiles + isa_align_up((size_t)BH * nQt * kBwdQTileBytes, 1024);
+  BwdPrepParams pp;
+  pp.q = q; pp.k = k; pp.v = v; pp.dout = dout; pp.out = out; pp.lse2 = lse2; pp.qtiles = qtiles; pp.ktiles = ktiles;
+  pp.BH = BH; pp.Lq = Lq; pp.Lk = Lk; pp.d = d; pp.dv = dv; pp.nQt = nQt; pp.nKt = nKt;
+  pp.qscale = 1.4426950408889634f / temperature;
+  attn_bwd_prep_kernel<<<dim3(nQt > nKt ? nQt : nKt, BH), 256, 0, stream>>>(pp);
+  ISA_CUDA(cudaGetLastError());
   BwdParams bp;
-  bp.q = q; bp.k = k; bp.v = v; bp.dout = dout; bp.out = out; bp.lse2 = lse2;
-  bp.key_mask = key_mask; bp.full_mask = full_mask; bp.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
-  bp.dq = dq; bp.dk = dk; bp.dv = dvv; bp.BH = BH; bp.Lq = Lq; bp.Lk = Lk; bp.d = d; bp.dv_dim = dv;
-  bp.qscale = 1.4426950408889634f / temperature; bp.inv_t = 1.f / temperature;
-  attn_bwd_kernel<<<dim3((Lk + kBwdK - 1) / kBwdK, BH), kBwdThreads, 0, stream>>>(bp, delta);
+  bp.qtiles = qtiles; bp.ktiles = ktiles;
+  bp.mask.key_mask = key_mask; bp.mask.full_mask = full_mask; bp.mask.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
+  bp.dq = dq; bp.dk = dk; bp.dv = dvv; bp.BH = BH; bp.Lq = Lq; bp.Lk = Lk; bp.d = d; bp.dv_dim = dv; bp.nQt = nQt; bp.nKt = nKt;
+  bp.inv_t = 1.f / temperature;
+  const size_t smem_dq = sizeof(DqSmem) + 1024, smem_dkv = sizeof(DkvSmem) + 1024;
+  ISA_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+  ISA_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv));
+  attn_bwd_dq_kernel<<<dim3(nQt, BH), kBwdThreads, smem_dq, stream>>>(bp);
+  attn_bwd_dkdv_kernel<<<dim3(nKt, BH), kBwdThreads, smem_dkv, stream>>>(bp);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }
