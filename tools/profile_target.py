@@ -55,3 +55,19 @@ if what in ("attn",):
         o, _ = scaled_dot_product_attention(q, k, v, 12 ** 0.5)
     torch.cuda.synchronize()
     print("attn", float(o.sum()))
+if what in ("train",):
+    from isa_b200.model import Model
+    from isa_b200.settings import CVPPPTrainingSettings
+    sys.path.insert(0, ROOT)
+    import bench
+    ts = CVPPPTrainingSettings()
+    torch.manual_seed(23)
+    model = Model('CVPPP', 'ReSeg', 2, 32, use_instance_segmentation=True, n_embedding=24, device=dev)
+    model.define_criterion(None, 0.5, 1.5, 2, False, 'Multi')
+    model.define_optimizer(1.0, 0.001, 0.5, 25, 'Adadelta')
+    img, sem, ins, labels, nobj = bench.train_batch(0, 16)
+    b = [torch.from_numpy(a).to(dev) for a in (img, sem, ins, nobj)]
+    for _ in range(3):
+        m = model.train_step(b[0], b[1], b[2], b[3], 10.0)
+    torch.cuda.synchronize()
+    print("train", float(m['Cost']))
