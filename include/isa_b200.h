@@ -154,8 +154,8 @@ int isa_attention_bwd(const float* q, const float* k, const float* v, const floa
  *   the arithmetic is PyTorch's nn.GRU: r,z = sigmoid(..), n = tanh(W_in x + b_in + r*(W_hn h + b_hn)),
  *   h' = (1-z)*n + z*h, weight_hh_l0 (3n, n) in gate order r,z,n).
  * All tensors are token-major ("channels last"):
- *   gx    [tokens][2][3n]  x W_ih^T + b_ih of both directions (one library GEMM by the caller)
- *   w_hh  [2][3n][n], b_hh [2][3n]
+ *   gx    [tokens][2][3n]  x W_ih^T (+ b_ih) of both directions (one GEMM by the caller)
+ *   w_hh  [2][3n][n], b_hh [2][3n]; b_ih [2][3n] or NULL when gx already carries the input-side bias
  *   out   [tokens][2n]     h_t of direction 0 in [0,n), of direction 1 (reverse sweep) in [n,2n)
  *   stash [tokens][2][4n]  r, z, n, (W_hn h + b_hn) kept for backward, or NULL for inference
  * Sequence q (0 <= q < n_seq) at step t lives at token
@@ -165,7 +165,7 @@ int isa_attention_bwd(const float* q, const float* k, const float* v, const floa
  * Backward writes dgx [tokens][2][3n] (gradient of the input projection; its r,z thirds are also the
  * hidden-side gate gradients) and dghn [tokens][2][n] (hidden-side n-gate gradient r*dn_pre);
  * weight/bias gradients are GEMMs / column sums over those (done by the caller). */
-int isa_gru_scan_fwd(const float* gx, const float* w_hh, const float* b_hh, int n_seq, int T, int n_units,
+int isa_gru_scan_fwd(const float* gx, const float* w_hh, const float* b_hh, const float* b_ih, int n_seq, int T, int n_units,
                      int inner, long long outer_tok_stride, long long inner_tok_stride, long long t_tok_stride,
                      float* out, float* stash, isa_stream_t stream);
 
@@ -173,6 +173,20 @@ int isa_gru_scan_bwd(const float* dout, const float* out, const float* stash, co
                      int n_seq, int T, int n_units,
                      int inner, long long outer_tok_stride, long long inner_tok_stride, long long t_tok_stride,
                      float* dgx, float* dghn, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ fp32 -> 3 x bf16 operand split
+ * The ReNet projections (x W_ih^T, dG W_ih, dG^T [x | h_prev | 1]) are plain GEMMs; they run on the bf16
+ * tensor pipe at fp32-level accuracy as  a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi  (one bf16 GEMM whose K
+ * dimension concatenates the three pairings, fp32 accumulate).  This writes the three parts of a row-major
+ * fp32 matrix src [rows][cols] (row stride src_ld) in one pass:
+ *   order 0 (left operand): (hi, hi, lo);  order 1 (right operand): (hi, lo, hi);
+ *   part q of element (r, c) -> dst[q * part_stride + r * dst_ld + c]   (bf16).
+ * pos_step != 0: read row r + shift instead and write zeros where the position (r / pos_div) % pos_mod
+ * plus pos_step leaves [0, pos_mod): h_{t-1} of a sweep direction straight from the forward output.
+ * cols, src_ld, dst_ld, part_stride: multiples of 4; src 16 B aligned. */
+int isa_split_bf16x3(const float* src, long long rows, int cols, long long src_ld, void* dst, long long dst_ld,
+                     long long part_stride, int order, long long shift, int pos_div, int pos_mod, int pos_step,
+                     isa_stream_t stream);
 
 #ifdef __cplusplus
 }

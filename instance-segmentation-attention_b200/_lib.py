@@ -66,12 +66,14 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     # ReNet GRU scan
-    "isa_gru_scan_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+    "isa_gru_scan_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_longlong, c_longlong, c_longlong,
                                  c_void_p, c_void_p, c_void_p]),
     "isa_gru_scan_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_longlong, c_longlong, c_longlong,
                                  c_void_p, c_void_p, c_void_p]),
+    "isa_split_bf16x3": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_longlong,
+                                 c_longlong, c_int, c_longlong, c_int, c_int, c_int, c_void_p]),
 }
 
 
@@ -84,7 +86,7 @@ KERNELS_PER_CALL = {
     "isa_disc_loss_fwd": 1, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1,
     "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
     "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 2,
-    "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1,
+    "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1, "isa_split_bf16x3": 1,
 }
 
 

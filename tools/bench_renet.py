@@ -49,6 +49,16 @@ def main():
     cols = torch.randn(B * W, H, 2 * n, device=dev)
     with torch.no_grad():
         res["cudnn_fwd_infer_ms"] = timeit(lambda: (gru1(rows), gru2(cols)))
+    # per-kernel device times of the scan entry points (CUDA events on the launching stream)
+    from isa_b200 import _lib
+    _lib.TIMER.enabled = True
+    _lib.TIMER.reset()
+    for _ in range(5):
+        f()
+        st["y"].backward(g)
+    for name, (cnt, ms) in _lib.TIMER.summary().items():
+        res[name + "_us_per_launch"] = 1e3 * ms / cnt
+    _lib.TIMER.enabled = False
     print(json.dumps(res))
 
 
