@@ -188,6 +188,59 @@ int isa_split_bf16x3(const float* src, long long rows, int cols, long long src_l
                      long long part_stride, int order, long long shift, int pos_div, int pos_mod, int pos_step,
                      isa_stream_t stream);
 
+/* ------------------------------------------------------------------ masked softmax over H*W
+ * Replaces the masked spatial softmaxes of the live attention layers:
+ *   /root/reference/code/lib/archs/modules/utils.py:507-512  SpatialAttentionLayer.forward
+ *       beta.masked_fill(1 - y, -inf) -> softmax over H*W -> * sum(y)          (K = 1, scale = sum(y), NaN kept)
+ *   /root/reference/code/lib/archs/modules/utils.py:648-652  HardAttentionLayer.forward
+ *       e_t.expand(-1, n, ..).masked_fill(1 - ins_seg, -inf) -> softmax over H*W -> NaN -> 0   (K = n instances)
+ * x     [B][HW] f32     one logit map per image, shared by its K masks
+ * mask  [B][K][HW]      mask_kind 0: u8, 1: f32; non-zero = pixel takes part
+ * scale [B*K] or NULL   multiplies row (b,k) of the result
+ * y     [B][K][HW]      softmax restricted to the mask, 0 elsewhere; a row whose mask is empty is NaN
+ *                       everywhere (what softmax over all -inf gives) or 0 everywhere with nan_to_zero
+ * stats [B*K][2]        (max, sum of exponentials) per row, needed by the backward call
+ * Backward: dx[b][p] = sum_k y[b][k][p] * (dy[b][k][p] - (sum_q y[b][k][q] dy[b][k][q]) / scale[b][k]);
+ * rows with an empty mask contribute nothing (masked_fill's backward zeroes them). */
+size_t isa_masked_softmax_hw_workspace_bytes(int B, int K, int HW);
+int isa_masked_softmax_hw_fwd(const float* x, const void* mask, int mask_kind, int B, int K, int HW, const float* scale,
+                              int nan_to_zero, float* y, float* stats, void* workspace, size_t workspace_bytes,
+                              isa_stream_t stream);
+int isa_masked_softmax_hw_bwd(const float* y, const float* dy, const float* stats, const float* scale, int B, int K, int HW,
+                              float* dx, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ row reductions / row affine
+ * The squeeze-excite channel attention (/root/reference/code/lib/archs/modules/utils.py:402-420 AttentionLayer):
+ * global average pool = row sums over H*W, x * gate = row affine; their gradients are the same two primitives.
+ *   isa_row_dot     out[r] = sum_p a[r][p] * b[r / b_rows_div][p]   (b NULL: plain row sums); deterministic two-stage
+ *   isa_row_affine  y[r][p] = x[r][p] * g[r] + c[r]                 (c NULL: 0) */
+size_t isa_row_dot_workspace_bytes(int rows, int HW);
+int isa_row_dot(const float* a, const float* b, int rows, int HW, int b_rows_div, float* out, void* workspace,
+                size_t workspace_bytes, isa_stream_t stream);
+int isa_row_affine(const float* x, const float* g, const float* c, int rows, int HW, float* y, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ single-query readout
+ * /root/reference/code/lib/archs/modules/utils.py:59-69 Decoder.forward: sigmoid(bmm(q (b,1,C), enc (b,C,HW))).
+ * q [B][C], enc [B][C][HW], out [B][HW].  Backward writes dz = dout * out * (1 - out) [B][HW] and, if denc is
+ * not NULL, denc[b][c][p] = q[b][c] * dz[b][p]; dq is isa_row_dot(enc, dz, B*C, HW, C). */
+int isa_readout_fwd(const float* q, const float* enc, int B, int C, int HW, float* out, isa_stream_t stream);
+int isa_readout_bwd(const float* q, const float* out, const float* dout, int B, int C, int HW, float* dz, float* denc,
+                    isa_stream_t stream);
+
+/* ------------------------------------------------------------------ local 3x3 dilated attention
+ * /root/reference/code/lib/archs/modules/utils.py:267-303 _ScalePDAttention.forward (the stencil part between the
+ * 1x1 projections and the output 1x1 convolution): per pixel, softmax over its nine dilated neighbours.
+ * Q, K [Bh][dk][h][w], V [Bh][dv][h][w] f32 (heads folded into the batch as the reference's .view does);
+ * nomask [mask_batches][h][w] f32 or NULL, non-zero = neighbour excluded; image b uses nomask[b % mask_batches]
+ * (the reference tiles the mask with .repeat(n_head,1,1,1), utils.py:272); out-of-image neighbours are zero padding
+ * that takes part with score 0 (utils.py:281-285).  out [Bh][dv][h][w]; P [Bh][9][h][w] = the probabilities, saved
+ * for backward (NULL at inference).  Backward needs a [Bh][9][h][w] f32 workspace. */
+int isa_local_attention_fwd(const float* Q, const float* K, const float* V, const float* nomask, int mask_batches, int Bh,
+                            int dk, int dv, int h, int w, int dil, float scale, float* out, float* P, isa_stream_t stream);
+int isa_local_attention_bwd(const float* Q, const float* K, const float* V, const float* P, const float* dout, int Bh,
+                            int dk, int dv, int h, int w, int dil, float scale, float* dQ, float* dK, float* dV,
+                            float* dS_workspace, isa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,21 @@ SIGNATURES = {
     "isa_gru_scan_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_longlong, c_longlong, c_longlong,
                                  c_void_p, c_void_p, c_void_p]),
+    # masked spatial softmaxes, SE primitives, readout, local attention
+    "isa_masked_softmax_hw_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "isa_masked_softmax_hw_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_masked_softmax_hw_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_row_dot_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "isa_row_dot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_row_affine": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "isa_readout_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "isa_readout_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "isa_local_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "isa_local_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "isa_split_bf16x3": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_longlong,
                                  c_longlong, c_int, c_longlong, c_int, c_int, c_int, c_void_p]),
 }
@@ -87,6 +102,8 @@ KERNELS_PER_CALL = {
     "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
     "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 2,
     "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1, "isa_split_bf16x3": 1,
+    "isa_masked_softmax_hw_fwd": 2, "isa_masked_softmax_hw_bwd": 3, "isa_row_dot": 2, "isa_row_affine": 1,
+    "isa_readout_fwd": 1, "isa_readout_bwd": 1, "isa_local_attention_fwd": 1, "isa_local_attention_bwd": 2,
 }
 
 

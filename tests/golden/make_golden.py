@@ -66,7 +66,7 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     if what in ("disc", "all"):
         gen_disc()
-    for extra in ("attn", "kmeans", "resize", "renet"):
+    for extra in ("attn", "kmeans", "resize", "renet", "spatial"):
         if what in (extra, "all"):
             mod = os.path.join(HERE, "make_golden_%s.py" % extra)
             if os.path.exists(mod):
