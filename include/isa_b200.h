@@ -34,6 +34,10 @@ typedef void* isa_stream_t; /* cudaStream_t */
 const char* isa_last_error(void);
 int isa_version(void);
 int isa_num_sms(int* out);
+/* Diagnostics: mean device time (us) of one grid-wide barrier between ctas_per_sm * num_sms co-resident CTAs
+ * (variant 0: fence per thread + sleeping poll, 1: cooperative-groups style) -- the fixed cost per iteration of the
+ * persistent cooperative kernels.  Synchronises the device; scratch = 8 bytes of device memory; result on the host. */
+int isa_selftest_grid_barrier(int ctas_per_sm, int threads, int iters, int variant, void* scratch, float* h_us_per_barrier);
 
 /* ------------------------------------------------------------------ discriminative loss
  * Replaces DiscriminativeLoss.forward + autograd backward:
@@ -49,7 +53,9 @@ int isa_num_sms(int* out);
  *            discriminative.py:153-159 (data parallel: global foreground count / world size, so that
  *            the rank-averaged loss equals the single-process loss of the whole batch)
  * out_loss [1], out_terms [4] = unweighted (var, dist, reg, qreg), out_means [bs][K][C]
- * workspace  isa_disc_loss_workspace_bytes(bs,C,K) bytes; hand the SAME buffer, untouched,
+ * A dense target is distilled once into a u8 label map kept in the workspace (1 byte per pixel for both passes);
+ * if some pixel is not one-hot (soft / overlapping masks) the kernels keep reading the dense masks.
+ * workspace  isa_disc_loss_workspace_bytes(bs,C,K,H,W) bytes; hand the SAME buffer, untouched,
  *            to isa_disc_loss_bwd (it carries the per-instance sums saved for backward).
  */
 #define ISA_TGT_LABEL_U8 0
@@ -57,7 +63,7 @@ int isa_num_sms(int* out);
 #define ISA_TGT_DENSE_I64 2
 #define ISA_TGT_DENSE_U8 3
 
-size_t isa_disc_loss_workspace_bytes(int bs, int C, int K);
+size_t isa_disc_loss_workspace_bytes(int bs, int C, int K, int H, int W);
 
 int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, const int* n_objects,
                       int bs, int C, int H, int W, int K,
@@ -93,7 +99,9 @@ int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int
  * init_centers device f32 [n_init][k][C] (array init; the data mean is subtracted like KMeans.fit does)
  * labels_out  [ld] i32 (first n valid), centers_out [k][C], inertia_out [n_init] f64, n_iter_out [n_init],
  * seed_idx_out [n_init][k] (k-means++ picks, may be NULL),
- * info        [4] i32: status (0 ok, 1 n<k, 2 non-finite input), best restart, n, Lloyd iterations run.
+ * info        [16] i32: status (0 ok, 1 n<k, 2 non-finite input), best restart, n, Lloyd (grid) iterations run;
+ *             [4..9] a coarse phase profile of the persistent Lloyd kernel as seen by CTA 0, in microseconds:
+ *             E-steps, barrier after them, centre updates, barrier after them, whole loop, tail (re-run, inertia, selection).
  */
 size_t isa_kmeans_workspace_bytes(int ld, int C, int k, int n_init);
 

@@ -27,8 +27,9 @@ SIGNATURES = {
     "isa_last_error": (ctypes.c_char_p, []),
     "isa_version": (c_int, []),
     "isa_num_sms": (c_int, [ctypes.POINTER(c_int)]),
+    "isa_selftest_grid_barrier": (c_int, [c_int, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_float)]),
     # discriminative loss
-    "isa_disc_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "isa_disc_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "isa_disc_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_float, c_int, c_int,
@@ -98,7 +99,7 @@ class IsaError(RuntimeError):
 
 # kernels launched per C-ABI call (memsets and copies not counted); used by bench.py's gpu_launches
 KERNELS_PER_CALL = {
-    "isa_disc_loss_fwd": 1, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1,
+    "isa_disc_loss_fwd": 2, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1,
     "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
     "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 2,
     "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1, "isa_split_bf16x3": 1,

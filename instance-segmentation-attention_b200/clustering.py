@@ -76,7 +76,7 @@ def kmeans_fit(Xt, n_dev, k, seed=0, n_init=35, max_iter=500, tol=1e-4, init_cen
     res.inertia = torch.empty(n_init, device=dev, dtype=torch.float64)
     res.n_iter = torch.empty(n_init, device=dev, dtype=torch.int32)
     res.seed_idx = torch.empty(n_init, k, device=dev, dtype=torch.int32)
-    res.info = torch.zeros(4, device=dev, dtype=torch.int32)
+    res.info = torch.zeros(16, device=dev, dtype=torch.int32)
     res.n_max = ld
     wsb = lib.isa_kmeans_workspace_bytes(ld, C, k, n_init)
     ws = torch.empty(wsb, device=dev, dtype=torch.uint8)

@@ -46,7 +46,9 @@ struct DiscWs {
   double* nfg;        // [1]
   unsigned* img_cnt;  // [bs]
   unsigned* done_cnt; // [1]
+  int* not_onehot;    // [1] dense target only: some pixel has several / non-unit entries -> keep the dense path
   // not zeroed
+  unsigned char* labels;  // [bs][P] u8 label map distilled from a dense one-hot target (255 = background)
   float* rnorm;   // [bs][K]  |mu~_k| before normalisation
   float* Nb;      // [bs]
   float* dist_b;  // [bs]
@@ -57,7 +59,7 @@ struct DiscWs {
   size_t total_bytes;
 };
 
-static DiscWs carve(void* base, int bs, int C, int K) {
+static DiscWs carve(void* base, int bs, int C, int K, int P) {
   DiscWs w;
   char* p = (char*)base;
   size_t off = 0;
@@ -73,7 +75,9 @@ static DiscWs carve(void* base, int bs, int C, int K) {
   w.var_sum = (float*)take(sizeof(float) * bs);
   w.img_cnt = (unsigned*)take(sizeof(unsigned) * bs);
   w.done_cnt = (unsigned*)take(sizeof(unsigned));
+  w.not_onehot = (int*)take(sizeof(int));
   w.zero_bytes = off;
+  w.labels = (unsigned char*)take((size_t)bs * P);
   w.rnorm = (float*)take(sizeof(float) * (size_t)bs * K);
   w.Nb = (float*)take(sizeof(float) * bs);
   w.dist_b = (float*)take(sizeof(float) * bs);
@@ -135,12 +139,40 @@ __device__ __forceinline__ float read_mask_k(const void* __restrict__ tgt, size_
   return 0.f;
 }
 
+// Warp-cooperative flush of the lanes' running (label, partial sums) into the CTA's shared accumulators.
+// Every lane parks its `width` partials in the warp's slab (row stride width | 1: conflict free); then, for each
+// distinct label held in the warp, lane c sums column c over the lanes holding that label and issues ONE shared
+// atomic -- instead of 32 lanes x width same-address atomics (which serialise 32-way and made the first
+// shared-memory version slower than flushing to L2).  Must be called by all 32 lanes.
 template <int CP>
-__device__ __forceinline__ void flush_run(float* __restrict__ dst_row, int stride_has_cnt, const float (&acc)[CP], float cnt, int C) {
+__device__ __forceinline__ void warp_flush(float* __restrict__ slab, float* __restrict__ dst, int dst_stride, int width, int cur,
+                                           const float (&acc)[CP], float cnt, int C) {
+  const int lane = threadIdx.x & 31;
+  const int SS = width | 1;
+  unsigned rem = __ballot_sync(0xffffffffu, cur >= 0);
+  if (rem == 0) return;
 #pragma unroll
   for (int c = 0; c < CP; ++c)
-    if (c < C) atomicAdd(dst_row + c, acc[c]);
-  if (stride_has_cnt) atomicAdd(dst_row + C, cnt);
+    if (c < C) slab[lane * SS + c] = acc[c];
+  if (width > C) slab[lane * SS + C] = cnt;
+  __syncwarp();
+  while (rem) {
+    const int leader = __ffs(rem) - 1;
+    const int L = __shfl_sync(0xffffffffu, cur, leader);
+    const unsigned grp = __ballot_sync(0xffffffffu, cur == L);
+    for (int col = lane; col < width; col += 32) {
+      float t = 0.f;
+      unsigned g = grp;
+      while (g) {
+        const int r = __ffs(g) - 1;
+        g &= g - 1;
+        t += slab[r * SS + col];
+      }
+      if (t != 0.f) atomicAdd(dst + (size_t)L * dst_stride + col, t);
+    }
+    rem &= ~grp;
+  }
+  __syncwarp();
 }
 
 // hinge on one (pixel, instance) pair: returns w*h^2 and the gradient scale so
@@ -166,13 +198,16 @@ __device__ __forceinline__ float hinge_pair(const float (&x)[CP], const float* _
 }
 
 template <int CP, int KIND>
-__global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(const FwdParams prm) {
-  extern __shared__ float smem[];  // means [K][CP+1]
+__device__ __forceinline__ void disc_fwd_body(const FwdParams& prm, const void* __restrict__ target) {
+  extern __shared__ float smem[];  // means [K][CP+1] | CTA-level sums [K][C+1] | CTA-level hinge-gradient sums [K][C]
   __shared__ float s_red[kWarps];
   __shared__ int s_flag;
   const int C = prm.C, K = prm.K, W = prm.W, H = prm.H, P = H * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int MS = CP + 1;
+  float* __restrict__ s_sum = smem + K * MS;            // [K][C+1]
+  float* __restrict__ s_gs = s_sum + K * (C + 1);       // [K][C]
+  float* __restrict__ slab = s_gs + K * C + warp * 32 * ((C + 1) | 1);   // per-warp [32][(C+1)|1] staging for warp_flush
 
   const int G = prm.G;
   const int b0 = blockIdx.x / G, g = blockIdx.x % G;
@@ -187,13 +222,18 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
     const float* __restrict__ emb = prm.emb + (size_t)b * C * P;
     const size_t img_off_px = (size_t)b * P;
     float* __restrict__ sums = prm.ws.sums + (size_t)b * K * (C + 1);
+    for (int i = threadIdx.x; i < K * (2 * C + 1); i += kThreads) s_sum[i] = 0.f;   // s_sum and s_gs are adjacent
+    __syncthreads();
 
     // ---------------- phase 1: per-instance sums, counts, q-regulariser ----------------
+    // runs are flushed to the CTA's shared-memory accumulators (native fp32 shared atomics); the CTA then adds
+    // its non-zero entries to the image's sums in L2 once -- r1a's version flushed every run straight to L2 and
+    // spent a third of the kernel waiting at the per-image barrier for those float atomics to drain
     for (int t = g * kWarps + warp; t < tiles; t += warps_per_img) {
       const int strip = t % prm.strips, rs = t / prm.strips;
       const int xcol = strip * 32 + lane;
       const int y0 = rs * prm.rpt, y1 = min(H, y0 + prm.rpt);
-      if (xcol >= W) continue;
+      const bool live = xcol < W;                       // dead lanes still take part in the warp-wide flushes
       float acc[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) acc[c] = 0.f;
@@ -203,36 +243,41 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
 #pragma unroll 2
       for (int y = y0; y < y1; ++y) {
         const int p = y * W + xcol;
-        int k1; float w1, fg;
-        const int nnz = read_mask<KIND>(prm.target, img_off_px, p, P, K, k1, w1, fg);
+        int k1 = -1; float w1 = 0.f, fg = 0.f;
+        int nnz = 0;
         float x[CP];
+        if (live) {
+          nnz = read_mask<KIND>(target, img_off_px, p, P, K, k1, w1, fg);
 #pragma unroll
-        for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
-        // q-regulariser: (|x*fg|_2 - 1)^2 for EVERY pixel (background adds 1).
-        float ss = 0.f;
+          for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
+          // q-regulariser: (|x*fg|_2 - 1)^2 for EVERY pixel (background adds 1).
+          float ss = 0.f;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) { const float tq = x[c] * fg; ss = fmaf(tq, tq, ss); }
-        const float l2 = sqrtf(ss);
-        q_tile += (l2 - 1.f) * (l2 - 1.f);
-        nfg_tile += fg;
-        if (nnz == 1) {
-          if (k1 < nb) {
-            if (k1 != cur) {
-              if (cur >= 0) flush_run<CP>(sums + (size_t)cur * (C + 1), 1, acc, cnt, C);
+          for (int c = 0; c < CP; ++c) { const float tq = x[c] * fg; ss = fmaf(tq, tq, ss); }
+          const float l2 = sqrtf(ss);
+          q_tile += (l2 - 1.f) * (l2 - 1.f);
+          nfg_tile += fg;
+        }
+        const bool single = (nnz == 1) && (k1 < nb);
+        // a lane whose run ends makes the whole warp flush (lanes in the middle of a run simply restart it);
+        // measured faster than letting that lane issue its C+1 shared atomics alone (146 vs 171 us at bs 16, 256^2)
+        if (__any_sync(0xffffffffu, single && cur >= 0 && k1 != cur)) {
+          warp_flush<CP>(slab, s_sum, C + 1, C + 1, cur, acc, cnt, C);
 #pragma unroll
-              for (int c = 0; c < CP; ++c) acc[c] = 0.f;
-              cnt = 0.f; cur = k1;
-            }
+          for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+          cnt = 0.f; cur = -1;
+        }
+        if (single) {
+          cur = k1;
 #pragma unroll
-            for (int c = 0; c < CP; ++c) acc[c] = fmaf(w1, x[c], acc[c]);
-            cnt += w1;
-          }
+          for (int c = 0; c < CP; ++c) acc[c] = fmaf(w1, x[c], acc[c]);
+          cnt += w1;
         } else if (nnz > 1) {
-          // soft / overlapping masks: every non-zero entry goes straight to L2.
+          // soft / overlapping masks: every non-zero entry goes straight to the shared accumulators.
           for (int k = k1; k < nb; ++k) {
-            const float m = read_mask_k<KIND>(prm.target, img_off_px, p, P, K, k);
+            const float m = read_mask_k<KIND>(target, img_off_px, p, P, K, k);
             if (m != 0.f) {
-              float* row = sums + (size_t)k * (C + 1);
+              float* row = s_sum + k * (C + 1);
 #pragma unroll
               for (int c = 0; c < CP; ++c) if (c < C) atomicAdd(row + c, m * x[c]);
               atomicAdd(row + C, m);
@@ -240,9 +285,14 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
           }
         }
       }
-      if (cur >= 0) flush_run<CP>(sums + (size_t)cur * (C + 1), 1, acc, cnt, C);
+      warp_flush<CP>(slab, s_sum, C + 1, C + 1, cur, acc, cnt, C);
       q_acc += (double)q_tile;
       nfg_acc += (double)nfg_tile;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * (C + 1); i += kThreads) {
+      const float v = s_sum[i];
+      if (v != 0.f) atomicAdd(sums + i, v);
     }
 
     // ---------------- per-image barrier ----------------
@@ -334,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
       const int strip = t % prm.strips, rs = t / prm.strips;
       const int xcol = strip * 32 + lane;
       const int y0 = rs * prm.rpt, y1 = min(H, y0 + prm.rpt);
-      if (xcol >= W) continue;
+      const bool live = xcol < W;
       float acc[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) acc[c] = 0.f;
@@ -342,39 +392,47 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
 #pragma unroll 2
       for (int y = y0; y < y1; ++y) {
         const int p = y * W + xcol;
-        int k1; float w1, fg;
-        const int nnz = read_mask<KIND>(prm.target, img_off_px, p, P, K, k1, w1, fg);
-        if (nnz == 0 || k1 >= nb) continue;
+        int k1 = -1; float w1 = 0.f, fg = 0.f;
+        int nnz = 0;
+        if (live) nnz = read_mask<KIND>(target, img_off_px, p, P, K, k1, w1, fg);
+        const bool use = nnz > 0 && k1 < nb;
+        const bool single = use && nnz == 1;
+        if (__any_sync(0xffffffffu, single && cur >= 0 && k1 != cur)) {
+          warp_flush<CP>(slab, s_gs, C, C, cur, acc, 0.f, C);
+#pragma unroll
+          for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+          cur = -1;
+        }
+        if (!use) continue;
         float x[CP];
 #pragma unroll
         for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
         float dir[CP]; float gs;
-        if (nnz == 1) {
+        if (single) {
           var_acc += hinge_pair<CP>(x, smem + k1 * MS, C, prm.norm, prm.delta_v, w1, dir, gs);
-          if (k1 != cur) {
-            if (cur >= 0) flush_run<CP>(gsum + (size_t)cur * C, 0, acc, 0.f, C);
-#pragma unroll
-            for (int c = 0; c < CP; ++c) acc[c] = 0.f;
-            cur = k1;
-          }
+          cur = k1;
 #pragma unroll
           for (int c = 0; c < CP; ++c) if (c < C) acc[c] = fmaf(gs, dir[c], acc[c]);
         } else {
           for (int k = k1; k < nb; ++k) {
-            const float m = read_mask_k<KIND>(prm.target, img_off_px, p, P, K, k);
+            const float m = read_mask_k<KIND>(target, img_off_px, p, P, K, k);
             if (m != 0.f) {
               var_acc += hinge_pair<CP>(x, smem + k * MS, C, prm.norm, prm.delta_v, m, dir, gs);
 #pragma unroll
-              for (int c = 0; c < CP; ++c) if (c < C) atomicAdd(gsum + (size_t)k * C + c, gs * dir[c]);
+              for (int c = 0; c < CP; ++c) if (c < C) atomicAdd(s_gs + k * C + c, gs * dir[c]);
             }
           }
         }
       }
-      if (cur >= 0) flush_run<CP>(gsum + (size_t)cur * C, 0, acc, 0.f, C);
+      warp_flush<CP>(slab, s_gs, C, C, cur, acc, 0.f, C);
     }
     var_acc = warp_sum(var_acc);
     if (lane == 0) s_red[warp] = var_acc;
     __syncthreads();
+    for (int i = threadIdx.x; i < K * C; i += kThreads) {
+      const float v = s_gs[i];
+      if (v != 0.f) atomicAdd(gsum + i, v);
+    }
     if (threadIdx.x == 0) {
       float v = 0.f;
       for (int w = 0; w < kWarps; ++w) v += s_red[w];
@@ -419,6 +477,20 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
       if (prm.w_q != 0.f) loss += prm.w_q * qreg;
       prm.out_loss[0] = loss;
     }
+  }
+}
+
+// A dense one-hot target (what the reference's collate emits: K x 4..8 bytes per pixel) is distilled once into a
+// u8 label map in the workspace (onehot_to_labels_kernel); forward and backward then read 1 byte per pixel.  If any
+// pixel turns out not to be one-hot (soft or overlapping masks) the flag is set and the kernels keep the dense path.
+template <int CP, int KIND>
+__global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(const FwdParams prm) {
+  if (KIND == TGT_LABEL_U8) {
+    disc_fwd_body<CP, TGT_LABEL_U8>(prm, prm.target);
+  } else if (__ldcg(prm.ws.not_onehot) == 0) {
+    disc_fwd_body<CP, TGT_LABEL_U8>(prm, prm.ws.labels);
+  } else {
+    disc_fwd_body<CP, KIND>(prm, prm.target);
   }
 }
 
@@ -518,7 +590,7 @@ __global__ void __launch_bounds__(128) disc_bwd_prep_kernel(const BwdParams prm)
 }
 
 template <int CP, int KIND>
-__global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm) {
+__device__ __forceinline__ void disc_bwd_body(const BwdParams& prm, const void* __restrict__ target) {
   extern __shared__ float sm[];  // mu [K][CP+1], T [K][CP+1]
   const int C = prm.C, K = prm.K, P = prm.H * prm.W;
   const int MS = CP + 1;
@@ -539,7 +611,7 @@ __global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm)
   const size_t img_off_px = (size_t)b * P;
   for (int p = blockIdx.x * kThreads + threadIdx.x; p < P; p += gridDim.x * kThreads) {
     int k1; float w1, fg;
-    const int nnz = read_mask<KIND>(prm.target, img_off_px, p, P, K, k1, w1, fg);
+    const int nnz = read_mask<KIND>(target, img_off_px, p, P, K, k1, w1, fg);
     float x[CP], gr[CP];
 #pragma unroll
     for (int c = 0; c < CP; ++c) x[c] = (c < C) ? __ldg(emb + (size_t)c * P + p) : 0.f;
@@ -561,7 +633,7 @@ __global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm)
       }
     } else if (nnz > 1) {
       for (int k = k1; k < nb; ++k) {
-        const float m = read_mask_k<KIND>(prm.target, img_off_px, p, P, K, k);
+        const float m = read_mask_k<KIND>(target, img_off_px, p, P, K, k);
         if (m != 0.f) {
           float dir[CP]; float gs;
           hinge_pair<CP>(x, s_mu + k * MS, C, prm.norm, prm.delta_v, m, dir, gs);
@@ -574,6 +646,17 @@ __global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm)
 #pragma unroll
     for (int c = 0; c < CP; ++c)
       if (c < C) gout[(size_t)c * P + p] = gr[c];
+  }
+}
+
+template <int CP, int KIND>
+__global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm) {
+  if (KIND == TGT_LABEL_U8) {
+    disc_bwd_body<CP, TGT_LABEL_U8>(prm, prm.target);
+  } else if (__ldcg(prm.ws.not_onehot) == 0) {
+    disc_bwd_body<CP, TGT_LABEL_U8>(prm, prm.ws.labels);
+  } else {
+    disc_bwd_body<CP, KIND>(prm, prm.target);
   }
 }
 
@@ -645,6 +728,18 @@ int launch_bwd(const BwdParams& prm, dim3 grid, size_t smem, cudaStream_t stream
   return ISA_OK;
 }
 
+int launch_onehot_to_labels(const void* target, int target_kind, int bs, int K, int P, unsigned char* labels, int* flag, int num_sms,
+                            cudaStream_t stream) {
+  const size_t total = (size_t)bs * P;
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms * 16) grid = num_sms * 16;
+  if (target_kind == TGT_DENSE_F32) onehot_to_labels_kernel<TGT_DENSE_F32><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag);
+  else if (target_kind == TGT_DENSE_I64) onehot_to_labels_kernel<TGT_DENSE_I64><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag);
+  else onehot_to_labels_kernel<TGT_DENSE_U8><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
 int pick_cp(int C) { return C <= 8 ? 8 : C <= 16 ? 16 : C <= 24 ? 24 : C <= 32 ? 32 : 64; }
 
 int check_common(int target_kind, int bs, int C, int H, int W, int K, int norm) {
@@ -661,9 +756,9 @@ int check_common(int target_kind, int bs, int C, int H, int W, int K, int norm) 
 
 extern "C" {
 
-size_t isa_disc_loss_workspace_bytes(int bs, int C, int K) {
-  if (bs <= 0 || C <= 0 || K <= 0) return 0;
-  return carve(nullptr, bs, C, K).total_bytes;
+size_t isa_disc_loss_workspace_bytes(int bs, int C, int K, int H, int W) {
+  if (bs <= 0 || C <= 0 || K <= 0 || H <= 0 || W <= 0) return 0;
+  return carve(nullptr, bs, C, K, H * W).total_bytes;
 }
 
 int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, const int* n_objects,
@@ -676,7 +771,7 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
   if (rc) return rc;
   ISA_CHECK_ARG(emb && target && n_objects && out_loss && out_terms && out_means && workspace, "disc_loss_fwd: null pointer");
   FwdParams prm;
-  prm.ws = carve(workspace, bs, C, K);
+  prm.ws = carve(workspace, bs, C, K, H * W);
   if (workspace_bytes < prm.ws.total_bytes) {
     isa_set_error("disc_loss_fwd: workspace %zu < required %zu bytes", workspace_bytes, prm.ws.total_bytes);
     return ISA_ERR_WORKSPACE;
@@ -691,7 +786,7 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
   prm.out_loss = out_loss; prm.out_terms = out_terms; prm.out_means = out_means; prm.q_den = q_den;
 
   const int CP = pick_cp(C);
-  const size_t smem = sizeof(float) * (size_t)K * (CP + 1);
+  const size_t smem = sizeof(float) * ((size_t)K * (CP + 1) + (size_t)K * (2 * C + 1) + (size_t)kWarps * 32 * ((C + 1) | 1));
   int occ = 0;
   switch (CP) {
     case 8: rc = occupancy_fwd<8>(target_kind, smem, &occ); break;
@@ -713,6 +808,10 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
   prm.rowsplits = (H + prm.rpt - 1) / prm.rpt;
 
   ISA_CUDA(cudaMemsetAsync(workspace, 0, prm.ws.zero_bytes, stream));
+  if (target_kind != TGT_LABEL_U8) {
+    rc = launch_onehot_to_labels(target, target_kind, bs, K, H * W, prm.ws.labels, prm.ws.not_onehot, di.num_sms, stream);
+    if (rc) return rc;
+  }
   switch (CP) {
     case 8: return launch_fwd<8>(prm, grid, smem, stream);
     case 16: return launch_fwd<16>(prm, grid, smem, stream);
@@ -732,7 +831,7 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
   if (rc) return rc;
   ISA_CHECK_ARG(emb && target && n_objects && means && grad_loss && grad_emb && workspace, "disc_loss_bwd: null pointer");
   BwdParams prm;
-  prm.ws = carve(workspace, bs, C, K);
+  prm.ws = carve(workspace, bs, C, K, H * W);
   if (workspace_bytes < prm.ws.total_bytes) {
     isa_set_error("disc_loss_bwd: workspace %zu < required %zu bytes", workspace_bytes, prm.ws.total_bytes);
     return ISA_ERR_WORKSPACE;
@@ -773,16 +872,11 @@ int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int
   ISA_CHECK_ARG(target_kind >= 1 && target_kind <= 3, "onehot_to_labels: target_kind %d is not a dense kind (1..3)", target_kind);
   ISA_CHECK_ARG(target && labels && not_onehot_flag, "onehot_to_labels: null pointer");
   ISA_CHECK_ARG(bs > 0 && K > 0 && K <= 254 && H > 0 && W > 0, "onehot_to_labels: bad dimensions");
-  const int P = H * W;
-  const size_t total = (size_t)bs * P;
-  int grid = (int)((total + 255) / 256);
-  if (grid > 148 * 16) grid = 148 * 16;
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
   ISA_CUDA(cudaMemsetAsync(not_onehot_flag, 0, sizeof(int), stream));
-  if (target_kind == TGT_DENSE_F32) onehot_to_labels_kernel<TGT_DENSE_F32><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, not_onehot_flag);
-  else if (target_kind == TGT_DENSE_I64) onehot_to_labels_kernel<TGT_DENSE_I64><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, not_onehot_flag);
-  else onehot_to_labels_kernel<TGT_DENSE_U8><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, not_onehot_flag);
-  ISA_CUDA(cudaGetLastError());
-  return ISA_OK;
+  return launch_onehot_to_labels(target, target_kind, bs, K, H * W, labels, not_onehot_flag, di.num_sms, stream);
 }
 
 }  // extern "C"

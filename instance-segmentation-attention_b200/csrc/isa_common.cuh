@@ -83,4 +83,16 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
   }
   __syncthreads();
 }
+// Leaner variant (the cooperative-groups pattern): bar.sync orders the CTA's writes before thread 0, whose
+// gpu-scope fence + release-arrive publishes them (fence cumulativity); no per-thread fence, no sleep in the poll.
+__device__ __forceinline__ void group_barrier_lean(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
 #endif

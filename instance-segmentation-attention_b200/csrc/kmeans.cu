@@ -26,13 +26,14 @@
 
 namespace {
 
+constexpr int kMaxL = 8;
 constexpr int kLloydThreads = 256;
 constexpr int kPPT = 4;                         // points per thread in the E-step
 constexpr int kTile = kLloydThreads * kPPT;     // points per work item
-constexpr int kSeedThreads = 512;
-constexpr int kMaxL = 8;
+constexpr int kSeedThreads = 256;
 constexpr int kMaxK = 254;
 constexpr int kMaxInit = 64;
+constexpr int kSeedMaxCtas = 512;
 
 struct KmScales {
   int S_mean, S_x, S_d, S_t;
@@ -44,7 +45,8 @@ struct KmWs {
   // header (zeroed)
   unsigned* maxabs_bits;   // [1]
   int* status;             // [1] 0 ok, 1 n<k, 2 non-finite
-  unsigned* barrier;       // [1]
+  unsigned* barrier;       // [1] grid barrier of the Lloyd kernel
+  unsigned* seed_barrier;  // [1] grid barrier of the seeding kernel (separate counter: both start from 0)
   long long* colsum;       // [C]
   long long* tolsum;       // [1]
   long long* sums;         // [R][k][C]
@@ -53,6 +55,7 @@ struct KmWs {
   int* changed;            // [R]
   int* state;              // [R] 0 active, 1 strict, 2 tol/max_iter
   int* n_iter;             // [R]
+  long long* seed_pot;     // [k][R][kMaxL] potentials of the candidates of every k-means++ step (atomically summed)
   size_t zero_bytes;
   // not zeroed
   float* mean;             // [C]
@@ -62,6 +65,8 @@ struct KmWs {
   unsigned char* labels;   // [R][ld]
   unsigned char* acct;     // [R][ld]
   int* seed_idx;           // [R][k]
+  long long* seed_tot;     // [R][kSeedMaxCtas] per-CTA totals of closest[] (fixed point)
+  int* seed_cand;          // [R][kMaxL] candidate indices of the current step
   size_t total_bytes;
 };
 
@@ -77,6 +82,7 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.maxabs_bits = (unsigned*)take(4);
   w.status = (int*)take(4);
   w.barrier = (unsigned*)take(4);
+  w.seed_barrier = (unsigned*)take(4);
   w.colsum = (long long*)take(8 * (size_t)C);
   w.tolsum = (long long*)take(8);
   w.sums = (long long*)take(8 * (size_t)R * k * C);
@@ -85,6 +91,7 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.changed = (int*)take(4 * (size_t)R);
   w.state = (int*)take(4 * (size_t)R);
   w.n_iter = (int*)take(4 * (size_t)R);
+  w.seed_pot = (long long*)take(8 * (size_t)k * R * kMaxL);
   w.zero_bytes = off;
   w.mean = (float*)take(4 * (size_t)C);
   w.Xc = (float*)take(4 * (size_t)C * ld);
@@ -93,6 +100,8 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.labels = (unsigned char*)take((size_t)R * ld);
   w.acct = (unsigned char*)take((size_t)R * ld);
   w.seed_idx = (int*)take(4 * (size_t)R * k);
+  w.seed_tot = (long long*)take(8 * (size_t)R * kSeedMaxCtas);
+  w.seed_cand = (int*)take(4 * (size_t)R * kMaxL);
   w.total_bytes = off;
   return w;
 }
@@ -129,6 +138,23 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// 64-bit add on shared memory as two native 32-bit atomics (a 64-bit shared atomicAdd compiles to a CAS loop,
+// ATOMS.CAST.SPIN): every adder learns from the returned low word whether ITS addition wrapped and forwards
+// that carry, so the final value is exact once all adders are done (read it after a barrier).
+__device__ __forceinline__ void smem_add64(long long* addr, long long v) {
+  unsigned* p = reinterpret_cast<unsigned*>(addr);
+  const unsigned lo = (unsigned)(unsigned long long)v, hi = (unsigned)((unsigned long long)v >> 32);
+  const unsigned old = atomicAdd(p, lo);
+  const unsigned add_hi = hi + ((old + lo < old) ? 1u : 0u);
+  if (add_hi) atomicAdd(p + 1, add_hi);
+}
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
@@ -213,152 +239,243 @@ __device__ inline int first_center_index(double u, int n) {
   return (int)i;
 }
 
+// warp sum of non-negative fixed-point values < 2^63 with three REDUX.SUMs on 21-bit limbs
+__device__ __forceinline__ long long warp_sum_q(long long q) {
+  const unsigned long long u = (unsigned long long)q;
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(u & 0x1FFFFFull));
+  const unsigned mi = __reduce_add_sync(0xffffffffu, (unsigned)((u >> 21) & 0x1FFFFFull));
+  const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(u >> 42));
+  return (long long)((unsigned long long)lo + ((unsigned long long)mi << 21) + ((unsigned long long)hi << 42));
+}
+
+// Greedy k-means++ for ALL restarts in one cooperative kernel.  The points are partitioned over the CTAs
+// (contiguous ranges, multiples of 32); every step of every restart is a pass over the CTA's own points:
+//   search   thresholds T = u * potential; the CTA whose range contains the crossing of the running
+//            prefix finds the candidate index (exact int64 prefix, warp scan)            -> grid barrier
+//   pass 1   potential of every (restart, trial) candidate: warp REDUX -> CTA -> one int64 atomic per
+//            (restart, trial) and CTA                                                    -> grid barrier
+//   pass 2   best trial per restart (argmin, first wins), closest = min(closest, d(best)),
+//            per-CTA totals for the next search                                          -> grid barrier
+// r1a's version ran one 512-thread CTA per restart (35 of 148 SMs busy, 9.5 ms); here every SM works on
+// every restart and the embedding tile of a CTA stays in L1 between passes.
 template <int CP>
-__global__ void __launch_bounds__(kSeedThreads, 1)
-km_seed_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, const double* __restrict__ uniforms, KmWs ws) {
+__global__ void __launch_bounds__(kSeedThreads, 2)
+km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, int R, const double* __restrict__ uniforms, KmWs ws) {
+  extern __shared__ __align__(16) unsigned char seed_smem[];
   const int n = *n_ptr;
   if (*ws.status) return;
-  const int r = blockIdx.x;
+  const int G = gridDim.x, b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = kSeedThreads / 32;
   const KmScales sc = km_scales(*ws.maxabs_bits, n, C);
-  const double* u = uniforms + (size_t)r * (1 + (k - 1) * L);
   const float* __restrict__ Xc = ws.Xc;
-  float* __restrict__ closest = ws.closest + (size_t)r * ld;
+  const int per = 1 + (k - 1) * L;
+  const int RL = R * L;
 
-  __shared__ float s_cand[kMaxL][64];
-  __shared__ long long s_wtot[NW];       // per-warp-segment total of the current closest[]
-  __shared__ long long s_wpre[NW + 1];   // exclusive prefix over segments
-  __shared__ long long s_pot[NW][kMaxL];
-  __shared__ long long s_Tq[kMaxL];
-  __shared__ int s_cidx[kMaxL];
-  __shared__ int s_best;
-  __shared__ long long s_potcur;
+  float* s_cand = reinterpret_cast<float*>(seed_smem);                         // [R][L][CP]
+  long long* s_pot = reinterpret_cast<long long*>(s_cand + (size_t)RL * CP);   // [NW][R*L]  (8 B aligned: RL*CP*4 is a multiple of 8)
+  long long* s_base = s_pot + (size_t)NW * RL;                                 // [R] exclusive prefix of this CTA
+  long long* s_total = s_base + R;                                             // [R] potential of restart r
+  long long* s_mytot = s_total + R;                                            // [R] this CTA's share
+  long long* s_Tq = s_mytot + R;                                               // [R*L] thresholds of the current step
+  int* s_best = reinterpret_cast<int*>(s_Tq + RL);                             // [R]
+  int* s_cidx = s_best + R;                                                    // [R*L] candidate indices of the current step
 
-  const int seg = ((n + NW - 1) / NW + 31) / 32 * 32;  // points per warp segment, multiple of 32
-  const int seg_lo = warp * seg, seg_hi = min(n, seg_lo + seg);
+  const int PT = ((n + G - 1) / G + 31) / 32 * 32;      // points per CTA
+  const int p_lo = min(n, b * PT), p_hi = min(n, p_lo + PT);
+  unsigned epoch = 0;
 
-  // ---- first centre
-  if (threadIdx.x == 0) { s_cidx[0] = first_center_index(u[0], n); ws.seed_idx[(size_t)r * k] = s_cidx[0]; }
-  __syncthreads();
-  if (threadIdx.x < C) s_cand[0][threadIdx.x] = Xc[(size_t)threadIdx.x * ld + s_cidx[0]];
-  __syncthreads();
-  {
-    long long tot = 0;
-    for (int i = seg_lo + lane; i < seg_hi; i += 32) {
-      float x[CP];
-#pragma unroll
-      for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + i] : 0.f;
-      const float d = sqdist_reg_smem<CP>(x, s_cand[0], C);
-      closest[i] = d;
-      tot += to_fixed(d, sc.p_d);
-    }
-    tot = warp_sum_ll(tot);
-    if (lane == 0) s_wtot[warp] = tot;
+  // ---- first centre of every restart (RandomState.choice), closest[] and per-CTA totals
+  for (int r = threadIdx.x; r < R; r += kSeedThreads) {
+    const int c0 = first_center_index(uniforms[(size_t)r * per], n);
+    s_best[r] = c0;
+    if (b == 0) ws.seed_idx[(size_t)r * k] = c0;
   }
   __syncthreads();
+  for (int idx = threadIdx.x; idx < R * CP; idx += kSeedThreads) {
+    const int r = idx / CP, f = idx % CP;
+    s_cand[(size_t)r * L * CP + f] = (f < C) ? Xc[(size_t)f * ld + s_best[r]] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < NW * RL; idx += kSeedThreads) s_pot[idx] = 0;
+  __syncthreads();
+  for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
+    const int i = i0 + threadIdx.x;
+    const bool ok = i < p_hi;
+    float x[CP];
+#pragma unroll
+    for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+    for (int r = 0; r < R; ++r) {
+      long long q = 0;
+      if (ok) {
+        const float d = sqdist_reg_smem<CP>(x, s_cand + (size_t)r * L * CP, C);
+        ws.closest[(size_t)r * ld + i] = d;
+        q = to_fixed(d, sc.p_d);
+      }
+      q = warp_sum_q(q);
+      if (lane == 0) s_pot[(size_t)warp * RL + r * L] += q;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += kSeedThreads) {
+    long long t = 0;
+    for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + r * L];
+    ws.seed_tot[(size_t)r * kSeedMaxCtas + b] = t;
+  }
+  if (b == 0)
+    for (int idx = threadIdx.x; idx < RL; idx += kSeedThreads) ws.seed_cand[idx] = n - 1;   // np.clip(candidate_ids, None, n-1)
+  grid_barrier(ws.seed_barrier, epoch);
 
   for (int c = 1; c < k; ++c) {
-    if (threadIdx.x == 0) {
-      long long p = 0;
-      for (int w = 0; w < NW; ++w) { s_wpre[w] = p; p += s_wtot[w]; }
-      s_wpre[NW] = p;
-      s_potcur = p;
+    // ---- search: prefix of the per-CTA totals, then the crossing inside this CTA's range.
+    //      All global reads of a thread are independent and issued together (one L2 round trip per phase).
+    for (int r = warp; r < R; r += NW) {
+      long long v[kSeedMaxCtas / 32];
+#pragma unroll
+      for (int j = 0; j < kSeedMaxCtas / 32; ++j) {
+        const int g = lane + 32 * j;
+        v[j] = (g < G) ? __ldcg(ws.seed_tot + (size_t)r * kSeedMaxCtas + g) : 0;
+      }
+      long long pre = 0, tot = 0, mine = 0;
+#pragma unroll
+      for (int j = 0; j < kSeedMaxCtas / 32; ++j) {
+        const int g = lane + 32 * j;
+        tot += v[j];
+        if (g < b) pre += v[j];
+        if (g == b) mine = v[j];
+      }
+      pre = warp_sum_ll(pre);
+      tot = warp_sum_ll(tot);
+      mine = warp_sum_ll(mine);
+      if (lane == 0) { s_base[r] = pre; s_total[r] = tot; s_mytot[r] = mine; }
     }
     __syncthreads();
-    if (threadIdx.x < L) {
-      const double T = __dmul_rn(u[1 + (c - 1) * L + threadIdx.x], __ll2double_rn(s_potcur));
-      s_Tq[threadIdx.x] = __double2ll_ru(T);
-      s_cidx[threadIdx.x] = n - 1;  // np.clip(candidate_ids, None, n-1)
+    // thresholds of every (restart, trial): T = u * potential, rounded up to the fixed-point grid
+    for (int pair = threadIdx.x; pair < RL; pair += kSeedThreads) {
+      const int r = pair / L, t = pair % L;
+      const double T = __dmul_rn(uniforms[(size_t)r * per + 1 + (c - 1) * L + t], __ll2double_rn(s_total[r]));
+      s_Tq[pair] = __double2ll_ru(T);
     }
     __syncthreads();
-    // searchsorted(cumsum, T, side='left'): the warp whose segment crosses T finds the index.
-    for (int t = 0; t < L; ++t) {
-      const long long Tq = s_Tq[t];
-      const long long lo = s_wpre[warp], hi = lo + s_wtot[warp];
-      // first segment whose inclusive prefix reaches Tq: lo < Tq <= hi, or Tq <= 0 for segment 0
-      const bool mine = (hi >= Tq) && (warp == 0 ? true : lo < Tq);
-      if (mine && seg_lo < n) {
+    for (int pair = warp; pair < RL; pair += NW) {
+      const int r = pair / L;
+      const long long Tq = s_Tq[pair];
+      const long long lo = s_base[r], hi = lo + s_mytot[r];
+      // first range whose inclusive prefix reaches Tq: lo < Tq <= hi, or Tq <= 0 for the first range
+      const bool mine = (p_lo < p_hi) && (hi >= Tq) && (b == 0 ? true : lo < Tq);
+      if (mine) {
+        const float* __restrict__ cl = ws.closest + (size_t)r * ld;
         long long base = lo;
-        for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
+        for (int i0 = p_lo; i0 < p_hi; i0 += 32) {
           const int i = i0 + lane;
-          long long q = (i < seg_hi) ? to_fixed(closest[i], sc.p_d) : 0;
-          // inclusive warp scan
+          long long q = (i < p_hi) ? to_fixed(cl[i], sc.p_d) : 0;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const long long y = __shfl_up_sync(0xffffffffu, q, o);
             if (lane >= o) q += y;
           }
-          const long long pre = base + q;
-          const unsigned hit = __ballot_sync(0xffffffffu, (i < seg_hi) && pre >= Tq);
+          const unsigned hit = __ballot_sync(0xffffffffu, (i < p_hi) && base + q >= Tq);
           if (hit) {
-            if (lane == 0) s_cidx[t] = i0 + (__ffs(hit) - 1);
+            if (lane == 0) ws.seed_cand[pair] = i0 + (__ffs(hit) - 1);
             break;
           }
           base += __shfl_sync(0xffffffffu, q, 31);
         }
       }
     }
+    grid_barrier(ws.seed_barrier, epoch);
+
+    // ---- pass 1: potential of every candidate over this CTA's points
+    for (int pair = threadIdx.x; pair < RL; pair += kSeedThreads) s_cidx[pair] = __ldcg(ws.seed_cand + pair);
+    for (int idx = threadIdx.x; idx < NW * RL; idx += kSeedThreads) s_pot[idx] = 0;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < L * C; idx += kSeedThreads) {
-      const int t = idx / C, f = idx % C;
-      s_cand[t][f] = Xc[(size_t)f * ld + s_cidx[t]];
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < RL * CP; idx += kSeedThreads) {
+      const int pair = idx / CP, f = idx % CP;
+      s_cand[idx] = (f < C) ? Xc[(size_t)f * ld + s_cidx[pair]] : 0.f;
     }
     __syncthreads();
-    // pass 1: potential of every candidate
-    long long pot[kMaxL];
-#pragma unroll
-    for (int t = 0; t < kMaxL; ++t) pot[t] = 0;
-    for (int i = seg_lo + lane; i < seg_hi; i += 32) {
+    for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
+      const int i = i0 + threadIdx.x;
+      const bool ok = i < p_hi;
       float x[CP];
 #pragma unroll
-      for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + i] : 0.f;
-      const float cl = closest[i];
-#pragma unroll
-      for (int t = 0; t < kMaxL; ++t)
-        if (t < L) pot[t] += to_fixed(fminf(cl, sqdist_reg_smem<CP>(x, s_cand[t], C)), sc.p_d);
-    }
-#pragma unroll
-    for (int t = 0; t < kMaxL; ++t)
-      if (t < L) {
-        const long long v = warp_sum_ll(pot[t]);
-        if (lane == 0) s_pot[warp][t] = v;
+      for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+      for (int r = 0; r < R; ++r) {
+        const float cl = ok ? ws.closest[(size_t)r * ld + i] : 0.f;
+        for (int t = 0; t < L; ++t) {
+          long long q = 0;
+          if (ok) q = to_fixed(fminf(cl, sqdist_reg_smem<CP>(x, s_cand + (size_t)(r * L + t) * CP, C)), sc.p_d);
+          q = warp_sum_q(q);
+          if (lane == 0) s_pot[(size_t)warp * RL + r * L + t] += q;
+        }
       }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    long long* pot_c = ws.seed_pot + (size_t)c * R * kMaxL;
+    for (int pair = threadIdx.x; pair < RL; pair += kSeedThreads) {
+      long long t = 0;
+      for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + pair];
+      if (t) atomicAdd((unsigned long long*)(pot_c + (pair / L) * kMaxL + pair % L), (unsigned long long)t);
+    }
+    grid_barrier(ws.seed_barrier, epoch);
+
+    // ---- best trial per restart; pass 2: closest = min(closest, d(best)), new per-CTA totals
+    for (int r = threadIdx.x; r < R; r += kSeedThreads) {
+      long long pv[kMaxL];
+#pragma unroll
+      for (int t = 0; t < kMaxL; ++t) pv[t] = (t < L) ? __ldcg(pot_c + r * kMaxL + t) : 0;
       int best = 0;
       long long bp = 0;
-      for (int t = 0; t < L; ++t) {
-        long long p = 0;
-        for (int w = 0; w < NW; ++w) p += s_pot[w][t];
-        if (t == 0 || p < bp) { bp = p; best = t; }
-      }
-      s_best = best;
-      ws.seed_idx[(size_t)r * k + c] = s_cidx[best];
-    }
-    __syncthreads();
-    // pass 2: closest = min(closest, d(best)), new segment totals
-    {
-      const int b = s_best;
-      long long tot = 0;
-      for (int i = seg_lo + lane; i < seg_hi; i += 32) {
-        float x[CP];
 #pragma unroll
-        for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + i] : 0.f;
-        const float nd = fminf(closest[i], sqdist_reg_smem<CP>(x, s_cand[b], C));
-        closest[i] = nd;
-        tot += to_fixed(nd, sc.p_d);
+      for (int t = 0; t < kMaxL; ++t)
+        if (t < L && (t == 0 || pv[t] < bp)) { bp = pv[t]; best = t; }
+      s_best[r] = best;
+      if (b == 0) ws.seed_idx[(size_t)r * k + c] = s_cidx[r * L + best];
+    }
+    for (int idx = threadIdx.x; idx < NW * RL; idx += kSeedThreads) s_pot[idx] = 0;
+    __syncthreads();
+    for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
+      const int i = i0 + threadIdx.x;
+      const bool ok = i < p_hi;
+      float x[CP];
+#pragma unroll
+      for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+      for (int r = 0; r < R; ++r) {
+        long long q = 0;
+        if (ok) {
+          float* cl = ws.closest + (size_t)r * ld + i;
+          const float nd = fminf(*cl, sqdist_reg_smem<CP>(x, s_cand + (size_t)(r * L + s_best[r]) * CP, C));
+          *cl = nd;
+          q = to_fixed(nd, sc.p_d);
+        }
+        q = warp_sum_q(q);
+        if (lane == 0) s_pot[(size_t)warp * RL + r * L] += q;
       }
-      tot = warp_sum_ll(tot);
-      if (lane == 0) s_wtot[warp] = tot;
     }
     __syncthreads();
+    for (int r = threadIdx.x; r < R; r += kSeedThreads) {
+      long long t = 0;
+      for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + r * L];
+      ws.seed_tot[(size_t)r * kSeedMaxCtas + b] = t;
+    }
+    __syncthreads();   // every thread is past its reads of seed_cand before CTA 0 resets it
+    if (b == 0)
+      for (int idx = threadIdx.x; idx < RL; idx += kSeedThreads) ws.seed_cand[idx] = n - 1;
+    grid_barrier(ws.seed_barrier, epoch);
   }
-  // centres of this restart = the picked rows
-  for (int idx = threadIdx.x; idx < k * C; idx += kSeedThreads) {
-    const int j = idx / C, f = idx % C;
-    ws.centers[((size_t)r * k + j) * C + f] = Xc[(size_t)f * ld + ws.seed_idx[(size_t)r * k + j]];
+  // centres of every restart = the picked rows (CTA 0 wrote seed_idx itself)
+  if (b == 0) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < R * k * C; idx += kSeedThreads) {
+      const int rj = idx / C, f = idx % C;
+      ws.centers[idx] = Xc[(size_t)f * ld + ws.seed_idx[rj]];
+    }
   }
+}
+
+size_t seed_smem_bytes(int R, int L, int CP) {
+  const size_t RL = (size_t)R * L;
+  return RL * CP * 4 + (size_t)(kSeedThreads / 32) * RL * 8 + 3 * (size_t)R * 8 + RL * 8 + (size_t)R * 4 + RL * 4 + 16;
 }
 
 // ------------------------------------------------------------------ Lloyd
@@ -371,7 +488,7 @@ struct LloydParams {
   float* centers_out;   // [k][C]
   double* inertia_out;  // [R]
   int* n_iter_out;      // [R]
-  int* info;            // [4] status, best restart, n, total Lloyd iterations
+  int* info;            // [16] status, best restart, n, total Lloyd iterations, then CTA 0's phase profile in us
 };
 
 // E-step of one tile: labels of kPPT points per thread against the centres in smem.
@@ -437,13 +554,13 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
   const KmWs& ws = prm.ws;
   const int status = *ws.status;
   if (status) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { prm.info[0] = status; prm.info[1] = 0; prm.info[2] = n; prm.info[3] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x < 16) prm.info[threadIdx.x] = threadIdx.x == 0 ? status : (threadIdx.x == 2 ? n : 0);
     return;
   }
   float* s_cent = reinterpret_cast<float*>(smem_raw);                       // [k][CP]
   float* s_csq = s_cent + k * CP;                                           // [k]
-  long long* s_sums = reinterpret_cast<long long*>(s_csq + ((k + 3) / 4 * 4 + 2) / 2 * 2);  // [k][C] (8B aligned)
-  int* s_cnt = reinterpret_cast<int*>(s_sums + (size_t)k * C);             // [k]
+  unsigned* s_moved = reinterpret_cast<unsigned*>(s_csq + (k + 3) / 4 * 4);  // [kTile] (point in tile | old << 12 | new << 20)
+  __shared__ int s_nmoved;
   __shared__ int s_active[kMaxInit];
   __shared__ int s_nactive;
   __shared__ long long s_redll[kLloydThreads / 32];
@@ -460,37 +577,26 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
   unsigned epoch = 0;
   int total_iters = 0;
 
-  auto zero_acc = [&]() {
-    for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) s_sums[idx] = 0;
-    for (int j = threadIdx.x; j < k; j += kLloydThreads) s_cnt[j] = 0;
-  };
-  auto flush_acc = [&](int r) {
-    for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) {
-      const long long v = s_sums[idx];
-      if (v) atomicAdd((unsigned long long*)(ws.sums + (size_t)r * k * C + idx), (unsigned long long)v);
-    }
-    for (int j = threadIdx.x; j < k; j += kLloydThreads) {
-      const int v = s_cnt[j];
-      if (v) atomicAdd(ws.cnt + (size_t)r * k + j, v);
-    }
-  };
-
-  // mode 0: Lloyd E-step with incremental M-step; mode 1: labels only (E-step re-run)
+  // mode 0: Lloyd E-step with incremental M-step; mode 1: labels only (E-step re-run).
+  // Incremental M-step: the points of a tile whose cluster changed are compacted into a shared list, then the
+  // whole CTA walks (entry, feature) pairs densely and moves each exact fixed-point contribution with native
+  // 64-bit global reductions (RED.ADD.64, fire and forget).  r1a did this per thread with 64-bit SHARED atomics
+  // (CAS loops) inside divergent code: every warp with one changed lane paid 2*C serialized atomics, and the
+  // E-steps took 9 of the kernel's 10 ms.
   auto run_estep = [&](int mode) {
     const int total = s_nactive * tiles;
-    const int ipc = (total + gridDim.x - 1) / gridDim.x;
-    const int it0 = blockIdx.x * ipc, it1 = min(total, it0 + ipc);
+    // balanced contiguous ranges (sizes differ by at most one item; ceil-sized ranges left up to half the CTAs idle)
+    const int it0 = (int)((long long)blockIdx.x * total / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
     int cur = -1;
     for (int item = it0; item < it1; ++item) {
       const int r = s_active[item / tiles], tile = item % tiles;
       if (r != cur) {
-        if (cur >= 0 && mode == 0) { __syncthreads(); flush_acc(cur); }
         __syncthreads();
         load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP);
-        if (mode == 0) zero_acc();
-        __syncthreads();
         cur = r;
       }
+      if (threadIdx.x == 0) s_nmoved = 0;
+      __syncthreads();
       int lab[kPPT];
       float x[kPPT][CP];
       estep_tile<CP>(Xc, ld, n, C, k, tile, s_cent, s_csq, lab, x);
@@ -499,43 +605,70 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
       bool any_changed = false;
 #pragma unroll
       for (int p = 0; p < kPPT; ++p) {
-        const int i = tile * kTile + p * kLloydThreads + threadIdx.x;
+        const int li = p * kLloydThreads + threadIdx.x;     // index inside the tile
+        const int i = tile * kTile + li;
+        bool moved = false;
+        int a = 255;
+        const int l = lab[p];
         if (i < n) {
-          const int l = lab[p];
           const int lp = labels[i];
           if (mode == 0) {
-            const int a = acct[i];
-            if (l != a) {
-#pragma unroll
-              for (int f = 0; f < CP; ++f)
-                if (f < C) {
-                  const long long q = to_fixed(x[p][f], sc.p_x);
-                  if (a != 255) atomicAdd((unsigned long long*)(s_sums + a * C + f), (unsigned long long)(-q));
-                  atomicAdd((unsigned long long*)(s_sums + l * C + f), (unsigned long long)q);
-                }
-              if (a != 255) atomicSub(s_cnt + a, 1);
-              atomicAdd(s_cnt + l, 1);
-              acct[i] = (unsigned char)l;
-            }
+            a = acct[i];
+            moved = (l != a);
+            if (moved) acct[i] = (unsigned char)l;
           }
           if (l != lp) { labels[i] = (unsigned char)l; any_changed = true; }
         }
+        if (mode == 0) {
+          const unsigned bal = __ballot_sync(0xffffffffu, moved);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nmoved, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (moved) s_moved[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)li | ((unsigned)a << 12) | ((unsigned)l << 20);
+          }
+        }
       }
-      if (mode == 0 && __syncthreads_or(any_changed) && threadIdx.x == 0) ws.changed[r] = 1;
+      const int any = __syncthreads_or(any_changed);        // also publishes s_moved / s_nmoved
+      if (mode == 0) {
+        if (any && threadIdx.x == 0) ws.changed[r] = 1;
+        const int nm = s_nmoved;
+        long long* gs = ws.sums + (size_t)r * k * C;
+        int* gcnt = ws.cnt + (size_t)r * k;
+        for (int idx = threadIdx.x; idx < nm * C; idx += kLloydThreads) {
+          const int e = idx / C, f = idx - e * C;
+          const unsigned ent = s_moved[e];
+          const int li = ent & 0xfff, a = (ent >> 12) & 0xff, l = (ent >> 20) & 0xff;
+          const long long q = to_fixed(Xc[(size_t)f * ld + tile * kTile + li], sc.p_x);
+          if (a != 255) atomicAdd((unsigned long long*)(gs + a * C + f), (unsigned long long)(-q));
+          atomicAdd((unsigned long long*)(gs + l * C + f), (unsigned long long)q);
+          if (f == 0) {
+            if (a != 255) atomicSub(gcnt + a, 1);
+            atomicAdd(gcnt + l, 1);
+          }
+        }
+      }
     }
-    if (cur >= 0 && mode == 0) { __syncthreads(); flush_acc(cur); }
   };
 
   auto rebuild_active = [&](int want_mode) {
-    // want_mode 0: state==0 (still iterating); 1: finished without strict convergence; 2: all
+    // want_mode 0: state==0 (still iterating); 1: finished without strict convergence; 2: all.
+    // One warp reads the states in parallel (r1a walked them with thread 0: R dependent L2 round trips per iteration).
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       int m = 0;
-      for (int r = 0; r < R; ++r) {
-        const int st = __ldcg(ws.state + r);
-        if ((want_mode == 0 && st == 0) || (want_mode == 1 && st == 2) || want_mode == 2) s_active[m++] = r;
+      for (int r0 = 0; r0 < R; r0 += 32) {
+        const int r = r0 + lane;
+        bool take = false;
+        if (r < R) {
+          const int st = __ldcg(ws.state + r);
+          take = (want_mode == 0 && st == 0) || (want_mode == 1 && st == 2) || want_mode == 2;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (take) s_active[m + __popc(bal & ((1u << lane) - 1u))] = r;
+        m += __popc(bal);
       }
-      s_nactive = m;
+      if (lane == 0) s_nactive = m;
     }
     __syncthreads();
   };
@@ -547,12 +680,19 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
   }
   grid_barrier(ws.barrier, epoch);
 
+  // CTA 0 keeps a coarse phase profile (ns): E-step, barrier after it, update, barrier after it
+  unsigned long long t_e = 0, t_b1 = 0, t_u = 0, t_b2 = 0, t_mark = gtime_ns();
+  const unsigned long long t_start = t_mark;
+  auto lap = [&](unsigned long long& acc) { const unsigned long long t = gtime_ns(); acc += t - t_mark; t_mark = t; };
+
   for (int it = 0; it < prm.max_iter; ++it) {
     rebuild_active(0);
     if (s_nactive == 0) break;
     ++total_iters;
     run_estep(0);
+    lap(t_e);
     grid_barrier(ws.barrier, epoch);
+    lap(t_b1);
 
     // ---- per-restart update: one CTA per active restart
     for (int a = blockIdx.x; a < s_nactive; a += gridDim.x) {
@@ -562,14 +702,19 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
       float* cen = ws.centers + (size_t)r * k * C;
       unsigned char* labels = ws.labels + (size_t)r * ld;
       unsigned char* acct = ws.acct + (size_t)r * ld;
-      // empty clusters (list fixed before any point moves)
+      // empty clusters (list fixed before any point moves): ascending list by ballot compaction
       __shared__ int s_empty[kMaxK + 2];
       __shared__ int s_nempty;
-      if (threadIdx.x == 0) {
+      if (warp == 0) {
         int m = 0;
-        for (int j = 0; j < k; ++j)
-          if (__ldcg(gc + j) == 0) s_empty[m++] = j;
-        s_nempty = m;
+        for (int j0 = 0; j0 < k; j0 += 32) {
+          const int j = j0 + lane;
+          const bool e = (j < k) && (__ldcg(gc + j) == 0);
+          const unsigned bal = __ballot_sync(0xffffffffu, e);
+          if (e) s_empty[m + __popc(bal & ((1u << lane) - 1u))] = j;
+          m += __popc(bal);
+        }
+        if (lane == 0) s_nempty = m;
       }
       __syncthreads();
       if (s_nempty > 0) {
@@ -628,11 +773,19 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
         const int cj = gc[j];
         if (cj > 0) s_new[j * CP + f] = __double2float_rn(__ddiv_rn(__dmul_rn(__ll2double_rn(gs[idx]), sc.ip_x), (double)cj));
       }
-      if (threadIdx.x == 0) {
-        int amax = 0;
-        for (int j = 1; j < k; ++j)
-          if (gc[j] > gc[amax]) amax = j;
-        s_misc[2] = amax;
+      if (warp == 0) {
+        // argmax of the counts, lowest index among equals (`gc[j] > gc[amax]` scanning upwards)
+        int bc = -1, bj = 0x7fffffff;
+        for (int j = lane; j < k; j += 32) {
+          const int cj = gc[j];
+          if (cj > bc) { bc = cj; bj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const int oc = __shfl_xor_sync(0xffffffffu, bc, o), oj = __shfl_xor_sync(0xffffffffu, bj, o);
+          if (oc > bc || (oc == bc && oj < bj)) { bc = oc; bj = oj; }
+        }
+        if (lane == 0) s_misc[2] = bj;
       }
       __syncthreads();
       for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) {
@@ -660,8 +813,11 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
       }
       __syncthreads();
     }
+    lap(t_u);
     grid_barrier(ws.barrier, epoch);
+    lap(t_b2);
   }
+  const unsigned long long t_loop_end = gtime_ns();
 
   // ---- E-step re-run for restarts that did not converge strictly
   rebuild_active(1);
@@ -672,8 +828,7 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
   rebuild_active(2);
   {
     const int total = R * tiles;
-    const int ipc = (total + gridDim.x - 1) / gridDim.x;
-    const int it0 = blockIdx.x * ipc, it1 = min(total, it0 + ipc);
+    const int it0 = (int)((long long)blockIdx.x * total / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
     int cur = -1;
     long long acc = 0;
     auto flush_inertia = [&](int r) {
@@ -740,19 +895,35 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
       prm.inertia_out[r] = __dmul_rn(__ll2double_rn(ws.inertia_q[r]), sc.ip_d);
       prm.n_iter_out[r] = ws.n_iter[r];
     }
-    if (threadIdx.x == 0) { prm.info[0] = 0; prm.info[1] = best; prm.info[2] = n; prm.info[3] = total_iters; }
+    if (threadIdx.x == 0) {
+      prm.info[0] = 0; prm.info[1] = best; prm.info[2] = n; prm.info[3] = total_iters;
+      prm.info[4] = (int)(t_e / 1000); prm.info[5] = (int)(t_b1 / 1000); prm.info[6] = (int)(t_u / 1000); prm.info[7] = (int)(t_b2 / 1000);
+      prm.info[8] = (int)((t_loop_end - t_start) / 1000); prm.info[9] = (int)((gtime_ns() - t_loop_end) / 1000);
+    }
   }
 }
 
 size_t lloyd_smem_bytes(int k, int C, int CP) {
-  size_t fl = (size_t)k * CP + ((k + 3) / 4 * 4 + 2) / 2 * 2;
-  return fl * 4 + (size_t)k * C * 8 + (size_t)k * 4 + 16;
+  size_t fl = (size_t)k * CP + (k + 3) / 4 * 4;
+  return fl * 4 + (size_t)kTile * 4 + 16;
 }
 
 template <int CP>
-int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, cudaStream_t stream) {
-  km_seed_kernel<CP><<<R, kSeedThreads, 0, stream>>>(n_ptr, ld, C, k, L, uniforms, ws);
-  ISA_CUDA(cudaGetLastError());
+int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, int num_sms, cudaStream_t stream) {
+  const size_t smem = seed_smem_bytes(R, L, CP);
+  const void* fn = (const void*)km_seed_coop_kernel<CP>;
+  if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSeedThreads, smem));
+  ISA_CHECK_ARG(occ >= 1, "kmeans: seeding kernel does not fit on an SM (smem %zu)", smem);
+  if (occ > 2) occ = 2;
+  int grid = num_sms * occ;
+  const int want = (ld + 127) / 128;       // no point in CTAs with fewer than ~128 points
+  if (grid > want) grid = want;
+  if (grid > kSeedMaxCtas) grid = kSeedMaxCtas;
+  if (grid < 1) grid = 1;
+  void* args[] = {(void*)&n_ptr, (void*)&ld, (void*)&C, (void*)&k, (void*)&L, (void*)&R, (void*)&uniforms, (void*)&ws};
+  ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kSeedThreads), args, smem, stream));
   return ISA_OK;
 }
 
@@ -816,11 +987,11 @@ int isa_kmeans_fit(const float* X, const int* n_ptr, int ld, int C, int k, int n
     ISA_CUDA(cudaGetLastError());
   } else {
     switch (CP) {
-      case 8: rc = launch_seed<8>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
-      case 16: rc = launch_seed<16>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
-      case 24: rc = launch_seed<24>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
-      case 32: rc = launch_seed<32>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
-      default: rc = launch_seed<64>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, stream); break;
+      case 8: rc = launch_seed<8>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, di.num_sms, stream); break;
+      case 16: rc = launch_seed<16>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, di.num_sms, stream); break;
+      case 24: rc = launch_seed<24>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, di.num_sms, stream); break;
+      case 32: rc = launch_seed<32>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, di.num_sms, stream); break;
+      default: rc = launch_seed<64>(n_ptr, ld, C, k, n_local_trials, n_init, uniforms, ws, di.num_sms, stream); break;
     }
     if (rc) return rc;
   }

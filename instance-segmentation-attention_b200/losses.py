@@ -66,7 +66,7 @@ class _DiscLossFn(torch.autograd.Function):
         loss = torch.empty((), device=x.device, dtype=torch.float32)
         terms_out = torch.empty(4, device=x.device, dtype=torch.float32)  # var, dist, reg, qreg
         means = torch.empty(bs, K, C, device=x.device, dtype=torch.float32)
-        ws_bytes = lib.isa_disc_loss_workspace_bytes(bs, C, K)
+        ws_bytes = lib.isa_disc_loss_workspace_bytes(bs, C, K, H, W)
         ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
         rc = lib.isa_disc_loss_fwd(
             _lib.ptr(x), _lib.ptr(tgt), kind, _lib.ptr(nobj), bs, C, H, W, K,

@@ -43,7 +43,7 @@ def main():
     means = torch.empty(bs, K, C, device=dev)
     grad = torch.empty_like(x)
     gl = torch.ones(1, device=dev)
-    wsb = lib.isa_disc_loss_workspace_bytes(bs, C, K)
+    wsb = lib.isa_disc_loss_workspace_bytes(bs, C, K, H, W)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     res = {"shape": [bs, C, H, W, K]}
