@@ -101,8 +101,8 @@ def algorithmic(name, cfg):
     n = 100
     if name == "isa_disc_loss_fwd":
         return "hbm", bs * HW * (4 * C_EMB + cfg["tgt_bytes"]) + bs * K_MAX * C_EMB * 4
-    if name == "isa_disc_loss_bwd":
-        return "hbm", bs * HW * (8 * C_EMB + cfg["tgt_bytes"])
+    if name == "isa_disc_loss_bwd":     # emb read + grad write + the 1 B/pixel label map distilled by the forward call
+        return "hbm", bs * HW * (8 * C_EMB + 1)
     if name == "isa_gru_scan_fwd":      # gx read + h write + stash write, both directions
         return "hbm", tok * 2 * (3 * n + n + 4 * n) * 4
     if name == "isa_gru_scan_bwd":      # dout + out + stash read, dgx + dghn write
@@ -113,7 +113,126 @@ def algorithmic(name, cfg):
     if name == "isa_attention_bwd":
         L = (NET_H // 4) * (NET_W // 4)
         return "tensor", 10.0 * (2 * bs) * L * L * 12
+    if name == "isa_split_bf16x3":      # fp32 read + 3 bf16 parts written, averaged over the calls of one step
+        return "hbm", cfg.get("split_bytes_per_call", 0.0)
     return None, 0.0
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `name`, from the committed
+    `ncu --set full` captures (profiles/r1_ncu_traffic.json); None when no capture exists for it."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def roofline_entry(name, n_calls, total_ms, cfg, peaks):
+    bound, units = algorithmic(name, cfg)
+    if bound is None or n_calls == 0 or total_ms <= 0:
+        return None
+    per_launch_s = total_ms / n_calls * 1e-3
+    if bound == "hbm":
+        ach, peak, unit = units / per_launch_s / 1e9, peaks["hbm"], "GB/s"
+    else:
+        ach, peak, unit = units / per_launch_s / 1e12, peaks["bf16"], "TFLOP/s"
+    return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+            "traffic": ncu_traffic(name), "peak_source": peaks["src"], "launches_timed": n_calls, "avg_launch_us": per_launch_s * 1e6}
+
+
+METRIC = "images/sec (pred.py inference, train step at 1/2/4/8 B200) vs host-CPU ref"
+INFER_WORKLOAD = ("pred.py inference: 530x500 RGB -> 256x256 -> ReSeg path -> softmax -> device k-means "
+                  "(k=16, n_init=35, max_iter=500, seed 0) -> masks at 530x500; batch 1 per GPU, replicas only")
+TRAIN_WORKLOAD = ("CVPPP-shaped training step: backbone + 2xReNet(100) + MHA(2 heads, d_k=12, L=4096) + heads + "
+                  "DiscriminativeLoss(C=24,K=32) + CE + Dice, fwd+bwd+clip+Adadelta, 256x256, batch 16 per GPU")
+
+
+def inference_leg(model, dev, peaks, steps, warmup, rank=0, world=1, sampler=None, timed=None, with_cpu=True):
+    """pred.py inference (configs[0]): value (inputs in HBM), e2e (host image in, host masks out), per-kernel times,
+    bit-exactness flags against the oracle / scikit-learn, and (N = 1) the host-CPU reference beside it."""
+    import torch
+    from isa_b200 import _lib, synth
+    from isa_b200.prediction import Prediction
+    from isa_b200.settings import CVPPPModelSettings
+    ms_ = CVPPPModelSettings()
+    pred = Prediction(ms_.IMAGE_HEIGHT, ms_.IMAGE_WIDTH, ms_.MEAN, ms_.STD, False, model, 1, seed=0)
+    raws = [synth.leaf_image(100 * rank + j, RAW_H, RAW_W) for j in range(4)]
+    tens = [pred.image_to_tensor(r)[0].unsqueeze(0).to(dev) for r in raws]
+    last = {}
+
+    def step_dev(i):
+        sem, emb = model.predict_device(tens[i % 4])
+        last["o"] = pred.cluster_device(sem[0], emb[0], N_OBJ, RAW_H, RAW_W)
+
+    def step_e2e(i):
+        last["masks"] = pred.predict_array(raws[i % 4])
+
+    if timed is None:
+        def timed(step_fn, n_steps, n_warm):
+            for i in range(n_warm):
+                step_fn(i)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(n_steps):
+                step_fn(n_warm + i)
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e)
+
+    _lib.TIMER.reset()
+    if sampler is not None:
+        sampler.start()
+    timed(step_dev, 0, warmup)
+    _lib.TIMER.enabled = True
+    ms = timed(step_dev, steps, 0)
+    _lib.TIMER.enabled = False
+    clocks = sampler.stop() if sampler is not None else None
+    summ = _lib.TIMER.summary()
+    launches = sum(_lib.KERNELS_PER_CALL[k] * c for k, (c, _) in summ.items())
+    ms_e2e = timed(step_e2e, steps, 1)
+    res = last["o"][4]
+    n_pts = int(res.info[2])
+    it_sum = int(res.n_iter.sum())
+    km = summ.get("isa_kmeans_fit", (1, 0.0))
+    per_launch_s = km[1] / max(km[0], 1) * 1e-3
+    units = it_sum * n_pts * (4 * C_EMB + 4)
+    ach = units / max(per_launch_s, 1e-12) / 1e9
+    total_img = world * steps
+    # parity flags against the oracle and the real scikit-learn on the last image (outside the timed region)
+    from oracle import kmeans as KM
+    sem, emb = model.predict_device(tens[(steps - 1) % 4])
+    fg, X = KM.gather_foreground(sem[0].cpu().numpy(), emb[0].cpu().numpy())
+    flags = {}
+    if rank == 0 and len(X) >= N_OBJ:
+        o = KM.kmeans_oracle(X, N_OBJ, seed=0)
+        got = pred.cluster_device(sem[0], emb[0], N_OBJ)[1].cpu().numpy()
+        flags["labels_identical_to_oracle"] = bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"])))
+        sk = KM.sklearn_fit_predict(X, N_OBJ, 0)
+        flags["labels_identical_to_sklearn_up_to_permutation"] = bool(KM.same_up_to_permutation(got[fg != 0], sk + 1))
+    leg = {
+        "value": total_img / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+        "config": {"workload": INFER_WORKLOAD,
+                   "l2": "4 alternating images; per-image working set (35 restarts x labels + X) < L2 by design",
+                   "fg_points": n_pts, "lloyd_restart_iterations": it_sum, "lloyd_grid_iterations": int(res.info[3]),
+                   "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in sorted(summ.items())}, **flags},
+        "e2e": {"value": total_img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 3 * NET_H * NET_W * 4,
+                "d2h_bytes_per_step": 2 * RAW_H * RAW_W},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "isa_kmeans_fit", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm"], "traffic": ncu_traffic("isa_kmeans_fit"), "peak_source": peaks["src"],
+                     "note": "X (n x 24 fp32) is L2 resident at this size; bytes = restart-iterations * n * (4C+4); "
+                             "restart-iterations/s = %.0f" % (it_sum / max(per_launch_s, 1e-12)),
+                     "avg_launch_us": per_launch_s * 1e6},
+    }
+    if clocks is not None:
+        leg["clocks"] = clocks
+    if with_cpu and rank == 0:
+        leg["cpu_baseline"] = cpu_reference("infer", steps=1, warmup=0)
+    return leg
 
 
 def run_ours(args):
@@ -189,95 +308,43 @@ def run_ours(args):
         ms_e2e = timed(step_e2e, args.steps, 1)
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         total_img = bs * world * args.steps
-        cfg = {"bs": bs, "tgt_bytes": 8 * K_MAX}
-        # dominant kernel among ours
+        tok = bs * (NET_H // 4) * (NET_W // 4)
+        # split calls of one step: forward x (256, 200 x3) + backward [dgx|dghn] (800) and [x|h|h] (cin+200) per sweep
+        split_elems = tok * ((256 + 3 * 200) + 4 * 800 + (256 + 3 * 200) + 4 * 200)
+        n_split = max(summ.get("isa_split_bf16x3", (1, 0))[0] // args.steps, 1)
+        cfg = {"bs": bs, "tgt_bytes": 8 * K_MAX, "split_bytes_per_call": split_elems * (4 + 6) / n_split}
+        # dominant kernel among ours, and the same figures for every timed entry point
         dom = max(summ.items(), key=lambda kv: kv[1][1])
-        bound, units = algorithmic(dom[0], cfg)
-        per_launch_s = dom[1][1] / dom[1][0] * 1e-3
-        if bound == "hbm":
-            ach, peak, unit = units / per_launch_s / 1e9, peaks["hbm"], "GB/s"
-        else:
-            ach, peak, unit = units / per_launch_s / 1e12, peaks["bf16"], "TFLOP/s"
+        dom_roof = roofline_entry(dom[0], dom[1][0], dom[1][1], cfg, peaks)
+        all_roof = [r for r in (roofline_entry(k_, v_[0], v_[1], cfg, peaks) for k_, v_ in sorted(summ.items())) if r]
         kernel_ms = {k: round(v[1] / args.steps, 4) for k, v in sorted(summ.items())}
         out = {
-            "metric": "images/sec (pred.py inference, train step at 1/2/4/8 B200) vs host-CPU ref",
+            "metric": METRIC,
             "value": total_img / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CVPPP-shaped training step: backbone + 2xReNet(100) + MHA(2 heads, d_k=12, L=4096) + heads + "
-                                   "DiscriminativeLoss(C=24,K=32) + CE + Dice, fwd+bwd+clip+Adadelta, 256x256, batch 16 per GPU",
+            "config": {"workload": TRAIN_WORKLOAD,
                        "per_gpu_batch": bs, "global_batch": bs * world, "parallelism": "dp%d" % world,
                        "l2": "working set (activations) >> 126 MB L2, two alternating input batches",
                        "target_format_value": "int64 one-hot (reference collate)", "kernel_ms_per_step": kernel_ms},
             "clocks": clocks,
             "e2e": {"value": total_img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
-            "roofline": {"kernel": dom[0], "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                         "traffic": None, "peak_source": peaks["src"], "launches_timed": dom[1][0],
-                         "avg_launch_us": per_launch_s * 1e6},
+            "roofline": dom_roof,
+            "rooflines": all_roof,
         }
+        if world == 1 and not args.no_inference:
+            out["inference"] = inference_leg(model, dev, peaks, steps=5, warmup=3)
     else:
-        ms_ = CVPPPModelSettings()
-        from isa_b200 import synth
-        pred = Prediction(ms_.IMAGE_HEIGHT, ms_.IMAGE_WIDTH, ms_.MEAN, ms_.STD, False, model, 1, seed=0)
-        raws = [synth.leaf_image(100 * rank + j, RAW_H, RAW_W) for j in range(4)]
-        tens = [pred.image_to_tensor(r)[0].unsqueeze(0).to(dev) for r in raws]
-        last = {}
-
-        def step_dev(i):
-            sem, emb = model.predict_device(tens[i % 4])
-            last["o"] = pred.cluster_device(sem[0], emb[0], N_OBJ, RAW_H, RAW_W)
-
-        def step_e2e(i):
-            last["masks"] = pred.predict_array(raws[i % 4])
-
-        _lib.TIMER.reset()
-        sampler.start()
-        timed(step_dev, 0, args.warmup)
-        _lib.TIMER.enabled = True
-        ms = timed(step_dev, args.steps, 0)
-        _lib.TIMER.enabled = False
-        clocks = sampler.stop()
-        summ = _lib.TIMER.summary()
-        launches = sum(_lib.KERNELS_PER_CALL[k] * c for k, (c, _) in summ.items())
-        ms_e2e = timed(step_e2e, args.steps, 1)
-        res = last["o"][4]
-        n_pts = int(res.info[2])
-        it_sum = int(res.n_iter.sum())
-        km = summ.get("isa_kmeans_fit", (1, 0.0))
-        per_launch_s = km[1] / max(km[0], 1) * 1e-3
-        units = it_sum * n_pts * (4 * C_EMB + 4)
-        ach = units / max(per_launch_s, 1e-12) / 1e9
-        total_img = world * args.steps
-        # parity flags against the oracle and the real scikit-learn on the last image (outside the timed region)
-        from oracle import kmeans as KM
-        sem, emb = model.predict_device(tens[(args.steps - 1) % 4])
-        fg, X = KM.gather_foreground(sem[0].cpu().numpy(), emb[0].cpu().numpy())
-        flags = {}
-        if rank == 0 and len(X) >= N_OBJ:
-            o = KM.kmeans_oracle(X, N_OBJ, seed=0)
-            got = pred.cluster_device(sem[0], emb[0], N_OBJ)[1].cpu().numpy()
-            flags["labels_identical_to_oracle"] = bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"])))
-            sk = KM.sklearn_fit_predict(X, N_OBJ, 0)
-            flags["labels_identical_to_sklearn_up_to_permutation"] = bool(KM.same_up_to_permutation(got[fg != 0], sk + 1))
+        leg = inference_leg(model, dev, peaks, steps=args.steps, warmup=args.warmup, rank=rank, world=world, sampler=sampler,
+                            timed=timed, with_cpu=False)
         out = {
-            "metric": "images/sec (pred.py inference, train step at 1/2/4/8 B200) vs host-CPU ref",
-            "value": total_img / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC,
+            "value": leg["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "pred.py inference: 530x500 RGB -> 256x256 -> ReSeg path -> softmax -> device k-means "
-                                   "(k=16, n_init=35, max_iter=500, seed 0) -> masks at 530x500; batch 1 per GPU, replicas only",
-                       "l2": "4 alternating images; per-image working set (35 restarts x labels + X) < L2 by design",
-                       "fg_points": n_pts, "lloyd_restart_iterations": it_sum,
-                       "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(summ.items())}, **flags},
-            "clocks": clocks,
-            "e2e": {"value": total_img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 3 * NET_H * NET_W * 4,
-                    "d2h_bytes_per_step": 2 * RAW_H * RAW_W},
-            "gpu_launches": launches,
-            "roofline": {"kernel": "isa_kmeans_fit", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                         "note": "X (n x 24 fp32) is L2 resident at this size; bytes = restart-iterations * n * (4C+4)",
-                         "avg_launch_us": per_launch_s * 1e6},
+            "config": leg["config"], "clocks": leg["clocks"], "e2e": leg["e2e"], "gpu_launches": leg["gpu_launches"],
+            "roofline": leg["roofline"],
         }
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_reference(args.workload, steps=1, warmup=0)
@@ -365,11 +432,12 @@ def run_reference(args):
     cb = cpu_reference(args.workload, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
     line = {
         "impl": "reference",
-        "metric": "images/sec (pred.py inference, train step at 1/2/4/8 B200) vs host-CPU ref",
+        "metric": METRIC,
         "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "host-CPU reference of the %s workload (see cpu_baseline.sample)" % args.workload},
+        "config": {"workload": TRAIN_WORKLOAD if args.workload == "train" else INFER_WORKLOAD,
+                   "arm": "host-CPU reference implementation of this workload, bounded sample (see cpu_baseline.sample)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -383,6 +451,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--no-inference", dest="no_inference", action="store_true",
+                    help="train workload: skip the extra pred.py inference leg reported under \"inference\" at N = 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

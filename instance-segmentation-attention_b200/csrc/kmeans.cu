@@ -23,13 +23,14 @@
 //                     update CTA -> grid barrier; then E-step re-run, inertia, selection.
 #include "isa_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kMaxL = 8;
 constexpr int kLloydThreads = 256;
-constexpr int kPPT = 4;                         // points per thread in the E-step
-constexpr int kTile = kLloydThreads * kPPT;     // points per work item
+constexpr int kMaxPPT = 4;                      // points per thread in the E-step (2 or 4)
+constexpr int kMaxTile = kLloydThreads * kMaxPPT;   // points per work item (upper bound)
 constexpr int kSeedThreads = 256;
 constexpr int kMaxK = 254;
 constexpr int kMaxInit = 64;
@@ -491,51 +492,73 @@ struct LloydParams {
   int* info;            // [16] status, best restart, n, total Lloyd iterations, then CTA 0's phase profile in us
 };
 
-// E-step of one tile: labels of kPPT points per thread against the centres in smem.
-template <int CP>
+typedef unsigned long long km_u64;
+__device__ __forceinline__ void km_ffma2(km_u64& acc, km_u64 a, km_u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ km_u64 km_pack2(float lo, float hi) {
+  km_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void km_unpack2(km_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+// E-step of one tile: labels of PPT points per thread against the centres in smem.  The dot products run on the
+// packed FP32 pipe (fma.rn.f32x2 -> FFMA2, two IEEE fmas per instruction, same rounding as __fmaf_rn): two points
+// of a thread share one accumulator pair, the centres sit in shared memory duplicated as {c, c} so one LDS.128
+// (warp broadcast) feeds two features.  A scalar FFMA issues every other cycle per scheduler on sm_100.
+template <int CP, int PPT>
 __device__ __forceinline__ void estep_tile(const float* __restrict__ Xc, int ld, int n, int C, int k, int tile,
-                                           const float* __restrict__ s_cent, const float* __restrict__ s_csq, int (&lab)[kPPT],
-                                           float (&x)[kPPT][CP]) {
-  const int base = tile * kTile + threadIdx.x;
+                                           const float* __restrict__ s_cdup, const float* __restrict__ s_csq, int (&lab)[PPT]) {
+  static_assert(PPT % 2 == 0, "points are processed in pairs");
+  constexpr int kTileP = kLloydThreads * PPT;
+  const int base = tile * kTileP + threadIdx.x;
+  km_u64 xp[PPT / 2][CP];
 #pragma unroll
-  for (int p = 0; p < kPPT; ++p) {
-    const int i = base + p * kLloydThreads;
+  for (int pp = 0; pp < PPT / 2; ++pp) {
+    const int i0 = base + (2 * pp) * kLloydThreads, i1 = i0 + kLloydThreads;
 #pragma unroll
-    for (int f = 0; f < CP; ++f) x[p][f] = (f < C && i < n) ? Xc[(size_t)f * ld + i] : 0.f;
+    for (int f = 0; f < CP; ++f) {
+      const float a = (f < C && i0 < n) ? Xc[(size_t)f * ld + i0] : 0.f;
+      const float b = (f < C && i1 < n) ? Xc[(size_t)f * ld + i1] : 0.f;
+      xp[pp][f] = km_pack2(a, b);
+    }
   }
-  float bv[kPPT];
+  float bv[PPT];
 #pragma unroll
-  for (int p = 0; p < kPPT; ++p) { bv[p] = 0.f; lab[p] = 0; }
+  for (int p = 0; p < PPT; ++p) { bv[p] = 0.f; lab[p] = 0; }
   for (int j = 0; j < k; ++j) {
-    const float* __restrict__ c = s_cent + j * CP;
-    float dot[kPPT];
+    const float* __restrict__ c = s_cdup + (size_t)j * 2 * CP;
+    km_u64 dot[PPT / 2];
 #pragma unroll
-    for (int p = 0; p < kPPT; ++p) dot[p] = 0.f;
+    for (int pp = 0; pp < PPT / 2; ++pp) dot[pp] = 0ull;
 #pragma unroll
-    for (int f4 = 0; f4 < CP; f4 += 4) {
-      const float4 cv = *reinterpret_cast<const float4*>(c + f4);
+    for (int f2 = 0; f2 < CP; f2 += 2) {
+      const ulonglong2 cv = *reinterpret_cast<const ulonglong2*>(c + 2 * f2);   // {c[f2], c[f2]}, {c[f2+1], c[f2+1]}
 #pragma unroll
-      for (int p = 0; p < kPPT; ++p) {
-        // zero padding beyond C is exact: fmaf(0, 0, acc) == acc
-        dot[p] = __fmaf_rn(x[p][f4 + 0], cv.x, dot[p]);
-        dot[p] = __fmaf_rn(x[p][f4 + 1], cv.y, dot[p]);
-        dot[p] = __fmaf_rn(x[p][f4 + 2], cv.z, dot[p]);
-        dot[p] = __fmaf_rn(x[p][f4 + 3], cv.w, dot[p]);
+      for (int pp = 0; pp < PPT / 2; ++pp) {
+        // zero padding beyond C is exact: fma(0, 0, acc) == acc
+        km_ffma2(dot[pp], xp[pp][f2], cv.x);
+        km_ffma2(dot[pp], xp[pp][f2 + 1], cv.y);
       }
     }
     const float cs = s_csq[j];
 #pragma unroll
-    for (int p = 0; p < kPPT; ++p) {
-      const float v = __fmaf_rn(-2.f, dot[p], cs);
-      if (j == 0 || v < bv[p]) { bv[p] = v; lab[p] = j; }
+    for (int pp = 0; pp < PPT / 2; ++pp) {
+      float d0, d1;
+      km_unpack2(dot[pp], d0, d1);
+      const float v0 = __fmaf_rn(-2.f, d0, cs), v1 = __fmaf_rn(-2.f, d1, cs);
+      if (j == 0 || v0 < bv[2 * pp]) { bv[2 * pp] = v0; lab[2 * pp] = j; }
+      if (j == 0 || v1 < bv[2 * pp + 1]) { bv[2 * pp + 1] = v1; lab[2 * pp + 1] = j; }
     }
   }
 }
 
-__device__ __forceinline__ void load_centers(const float* __restrict__ gc, float* s_cent, float* s_csq, int k, int C, int CP) {
+__device__ __forceinline__ void load_centers(const float* __restrict__ gc, float* s_cent, float* s_csq, int k, int C, int CP,
+                                             float* s_cdup = nullptr) {
   for (int idx = threadIdx.x; idx < k * CP; idx += kLloydThreads) {
     const int j = idx / CP, f = idx % CP;
-    s_cent[idx] = (f < C) ? __ldcg(gc + (size_t)j * C + f) : 0.f;
+    const float v = (f < C) ? __ldcg(gc + (size_t)j * C + f) : 0.f;
+    s_cent[idx] = v;
+    if (s_cdup) *reinterpret_cast<float2*>(s_cdup + 2 * idx) = make_float2(v, v);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < k; j += kLloydThreads) {
@@ -546,8 +569,10 @@ __device__ __forceinline__ void load_centers(const float* __restrict__ gc, float
   __syncthreads();
 }
 
-template <int CP>
-__global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydParams prm) {
+template <int CP, int PPT>
+__global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kernel(const LloydParams prm) {
+  constexpr int kPPT = PPT;
+  constexpr int kTile = kLloydThreads * PPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = *prm.n_ptr;
   const int C = prm.C, k = prm.k, R = prm.R, ld = prm.ld;
@@ -559,7 +584,8 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
   }
   float* s_cent = reinterpret_cast<float*>(smem_raw);                       // [k][CP]
   float* s_csq = s_cent + k * CP;                                           // [k]
-  unsigned* s_moved = reinterpret_cast<unsigned*>(s_csq + (k + 3) / 4 * 4);  // [kTile] (point in tile | old << 12 | new << 20)
+  float* s_cdup = s_csq + (k + 3) / 4 * 4;                                  // [k][CP] x {c, c} (16 B aligned)
+  unsigned* s_moved = reinterpret_cast<unsigned*>(s_cdup + (size_t)2 * k * CP);  // [kTile] (point in tile | old << 12 | new << 20)
   __shared__ int s_nmoved;
   __shared__ int s_active[kMaxInit];
   __shared__ int s_nactive;
@@ -592,32 +618,37 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
       const int r = s_active[item / tiles], tile = item % tiles;
       if (r != cur) {
         __syncthreads();
-        load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP);
+        load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP, s_cdup);
         cur = r;
       }
       if (threadIdx.x == 0) s_nmoved = 0;
       __syncthreads();
-      int lab[kPPT];
-      float x[kPPT][CP];
-      estep_tile<CP>(Xc, ld, n, C, k, tile, s_cent, s_csq, lab, x);
       unsigned char* labels = ws.labels + (size_t)r * ld;
       unsigned char* acct = ws.acct + (size_t)r * ld;
+      // previous labels / accounted clusters are fetched before the distance loop so their latency hides behind it
+      int lprev[kPPT], aprev[kPPT];
+#pragma unroll
+      for (int p = 0; p < kPPT; ++p) {
+        const int i = tile * kTile + p * kLloydThreads + threadIdx.x;
+        lprev[p] = (i < n) ? labels[i] : 0;
+        aprev[p] = (i < n && mode == 0) ? acct[i] : 255;
+      }
+      int lab[kPPT];
+      estep_tile<CP, PPT>(Xc, ld, n, C, k, tile, s_cdup, s_csq, lab);
       bool any_changed = false;
 #pragma unroll
       for (int p = 0; p < kPPT; ++p) {
         const int li = p * kLloydThreads + threadIdx.x;     // index inside the tile
         const int i = tile * kTile + li;
         bool moved = false;
-        int a = 255;
+        const int a = aprev[p];
         const int l = lab[p];
         if (i < n) {
-          const int lp = labels[i];
           if (mode == 0) {
-            a = acct[i];
             moved = (l != a);
             if (moved) acct[i] = (unsigned char)l;
           }
-          if (l != lp) { labels[i] = (unsigned char)l; any_changed = true; }
+          if (l != lprev[p]) { labels[i] = (unsigned char)l; any_changed = true; }
         }
         if (mode == 0) {
           const unsigned bal = __ballot_sync(0xffffffffu, moved);
@@ -904,8 +935,8 @@ __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_kernel(const LloydP
 }
 
 size_t lloyd_smem_bytes(int k, int C, int CP) {
-  size_t fl = (size_t)k * CP + (k + 3) / 4 * 4;
-  return fl * 4 + (size_t)kTile * 4 + 16;
+  size_t fl = (size_t)3 * k * CP + (k + 3) / 4 * 4;
+  return fl * 4 + (size_t)kMaxTile * 4 + 16;
 }
 
 template <int CP>
@@ -927,10 +958,10 @@ int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const doub
   return ISA_OK;
 }
 
-template <int CP>
-int launch_lloyd(const LloydParams& prm, int num_sms, cudaStream_t stream) {
+template <int CP, int PPT>
+int launch_lloyd_ppt(const LloydParams& prm, int num_sms, cudaStream_t stream) {
   const size_t smem = lloyd_smem_bytes(prm.k, prm.C, CP);
-  const void* fn = (const void*)km_lloyd_kernel<CP>;
+  const void* fn = (const void*)km_lloyd_kernel<CP, PPT>;
   if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLloydThreads, smem));
@@ -939,6 +970,17 @@ int launch_lloyd(const LloydParams& prm, int num_sms, cudaStream_t stream) {
   void* args[] = {(void*)&prm};
   ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms * occ), dim3(kLloydThreads), args, smem, stream));
   return ISA_OK;
+}
+
+// 2 points per thread and two CTAs per SM (one CTA's loads overlap the other's distance loop) unless the embedding
+// is too wide for 128 registers; ISA_KM_PPT=2|4 overrides (experiments).
+template <int CP>
+int launch_lloyd(const LloydParams& prm, int num_sms, cudaStream_t stream) {
+  int ppt = (CP <= 32) ? 2 : 4;
+  const char* e = getenv("ISA_KM_PPT");
+  if (e && (e[0] == '2' || e[0] == '4')) ppt = e[0] - '0';
+  if (ppt == 2) return launch_lloyd_ppt<CP, 2>(prm, num_sms, stream);
+  return launch_lloyd_ppt<CP, 4>(prm, num_sms, stream);
 }
 
 int pick_cp(int C) { return C <= 8 ? 8 : C <= 16 ? 16 : C <= 24 ? 24 : C <= 32 ? 32 : 64; }
