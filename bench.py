@@ -167,8 +167,16 @@ def inference_leg(model, dev, peaks, steps, warmup, rank=0, world=1, sampler=Non
         sem, emb = model.predict_device(tens[i % 4])
         last["o"] = pred.cluster_device(sem[0], emb[0], N_OBJ, RAW_H, RAW_W)
 
+    def _raw_cycle():
+        j = 0
+        while True:
+            yield raws[j % 4]
+            j += 1
+
+    e2e_results = pred.predict_many(_raw_cycle())    # the pipelined public path pred_list.py uses
+
     def step_e2e(i):
-        last["masks"] = pred.predict_array(raws[i % 4])
+        last["masks"] = next(e2e_results)            # host image in -> host uint8 masks out
 
     if timed is None:
         def timed(step_fn, n_steps, n_warm):
@@ -213,6 +221,7 @@ def inference_leg(model, dev, peaks, steps, warmup, rank=0, world=1, sampler=Non
         flags["labels_identical_to_oracle"] = bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"])))
         sk = KM.sklearn_fit_predict(X, N_OBJ, 0)
         flags["labels_identical_to_sklearn_up_to_permutation"] = bool(KM.same_up_to_permutation(got[fg != 0], sk + 1))
+        flags["sklearn_partition_agreement"] = KM.partition_agreement(got[fg != 0], sk + 1)
     leg = {
         "value": total_img / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
         "config": {"workload": INFER_WORKLOAD,
@@ -290,8 +299,22 @@ def run_ours(args):
             b = devb[i % n_host]
             last["m"] = model.train_step(b[0], b[1], b[2], b[3], clip)
 
+        from isa_b200.data import CudaPrefetcher
+
+        class _Cycle(object):                        # an endless loader over the pinned host batches
+            def __iter__(self):
+                j = 0
+                while True:
+                    yield host[j % n_host]
+                    j += 1
+
+            def __len__(self):
+                return 1 << 30
+
+        e2e_batches = iter(CudaPrefetcher(_Cycle(), dev))   # the public staging path Model.fit uses (data.py)
+
         def step_e2e(i):
-            b = host[i % n_host]
+            b = next(e2e_batches)                    # H2D of this step's pinned inputs (overlaps the previous step)
             m = model.train_step(b[0], b[1], b[2], b[3], clip)
             last["loss"] = float(m['Cost'])          # device -> host read of the step's result
 
@@ -334,7 +357,14 @@ def run_ours(args):
             "rooflines": all_roof,
         }
         if world == 1 and not args.no_inference:
-            out["inference"] = inference_leg(model, dev, peaks, steps=5, warmup=3)
+            # pred.py runs a checkpoint, not the net this bench has just trained for a few steps: a fresh model with
+            # the settings' seed, i.e. exactly what `--workload infer` measures
+            del model
+            torch.cuda.empty_cache()
+            torch.manual_seed(ts.SEED)
+            infer_model = Model('CVPPP', 'ReSeg', ts.N_CLASSES, ts.MAX_N_OBJECTS, use_instance_segmentation=True,
+                                n_embedding=C_EMB, device=dev)
+            out["inference"] = inference_leg(infer_model, dev, peaks, steps=5, warmup=3)
     else:
         leg = inference_leg(model, dev, peaks, steps=args.steps, warmup=args.warmup, rank=rank, world=world, sampler=sampler,
                             timed=timed, with_cpu=False)

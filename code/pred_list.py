@@ -26,7 +26,16 @@ if __name__ == '__main__':
         images_list = images_list[:, 0]
     image_names = [os.path.splitext(os.path.basename(p))[0] for p in images_list]
     model, prediction = _common.build_model_and_prediction(opt.dataset, opt.model, opt.seed)
-    for image_name, image_path in zip(image_names, images_list):
-        image, fg_seg_pred, ins_seg_pred, n_objects_pred = prediction.predict(str(image_path))
+    from PIL import Image
+    raws = (np.array(Image.open(str(p)).convert('RGB')) for p in images_list)
+    kept = []
+
+    def tee():                      # predict_many consumes the images in a worker thread; keep them for the writer
+        for r in raws:
+            kept.append(r)
+            yield r
+
+    for image_name, (fg_seg_pred, ins_seg_pred, n_objects_pred) in zip(image_names, prediction.predict_many(tee())):
+        image = kept.pop(0)
         _common.write_prediction(os.path.join(opt.output, image_name), image_name, image, fg_seg_pred, ins_seg_pred, n_objects_pred)
     print('wrote %d predictions under %s' % (len(image_names), opt.output))

@@ -221,12 +221,20 @@ __global__ void km_init_centers_kernel(const float* __restrict__ init, int R, in
 }
 
 // ------------------------------------------------------------------ seeding
+// squared distance of a point in registers to a vector in shared memory; both are zero padded beyond C, which is
+// exact (fma(0, 0, acc) == acc), so the loop is branch free and reads the vector with 16-byte loads
 template <int CP>
 __device__ __forceinline__ float sqdist_reg_smem(const float (&x)[CP], const float* __restrict__ c, int C) {
   float acc = 0.f;
+  (void)C;
 #pragma unroll
-  for (int f = 0; f < CP; ++f)
-    if (f < C) { const float t = __fsub_rn(x[f], c[f]); acc = __fmaf_rn(t, t, acc); }
+  for (int f4 = 0; f4 < CP; f4 += 4) {
+    const float4 cv = *reinterpret_cast<const float4*>(c + f4);
+    float t = __fsub_rn(x[f4], cv.x); acc = __fmaf_rn(t, t, acc);
+    t = __fsub_rn(x[f4 + 1], cv.y); acc = __fmaf_rn(t, t, acc);
+    t = __fsub_rn(x[f4 + 2], cv.z); acc = __fmaf_rn(t, t, acc);
+    t = __fsub_rn(x[f4 + 3], cv.w); acc = __fmaf_rn(t, t, acc);
+  }
   return acc;
 }
 
@@ -259,7 +267,10 @@ __device__ __forceinline__ long long warp_sum_q(long long q) {
 //            per-CTA totals for the next search                                          -> grid barrier
 // r1a's version ran one 512-thread CTA per restart (35 of 148 SMs busy, 9.5 ms); here every SM works on
 // every restart and the embedding tile of a CTA stays in L1 between passes.
-template <int CP>
+// RES (tile-resident): the launch has at least ceil(ld / 256) CTAs, so every CTA owns at most 256 points = one point
+// per thread: the point's features stay in REGISTERS and closest[] of all restarts in shared memory for the whole
+// seeding, and warps without points skip the passes.
+template <int CP, bool RES>
 __global__ void __launch_bounds__(kSeedThreads, 2)
 km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, int R, const double* __restrict__ uniforms, KmWs ws) {
   extern __shared__ __align__(16) unsigned char seed_smem[];
@@ -281,6 +292,7 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   long long* s_Tq = s_mytot + R;                                               // [R*L] thresholds of the current step
   int* s_best = reinterpret_cast<int*>(s_Tq + RL);                             // [R]
   int* s_cidx = s_best + R;                                                    // [R*L] candidate indices of the current step
+  float* s_cl = reinterpret_cast<float*>(s_cidx + RL + (RL & 1));              // RES: [R][kSeedThreads] closest[] of this CTA's points
 
   const int PT = ((n + G - 1) / G + 31) / 32 * 32;      // points per CTA
   const int p_lo = min(n, b * PT), p_hi = min(n, p_lo + PT);
@@ -299,6 +311,28 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   }
   for (int idx = threadIdx.x; idx < NW * RL; idx += kSeedThreads) s_pot[idx] = 0;
   __syncthreads();
+  // RES: this thread's point for the whole kernel
+  const int my_i = p_lo + threadIdx.x;
+  const bool my_ok = my_i < p_hi;
+  const bool warp_ok = (p_lo + warp * 32) < p_hi;       // warps without points skip the passes
+  float xr[CP];
+  if (RES) {
+#pragma unroll
+    for (int f = 0; f < CP; ++f) xr[f] = (my_ok && f < C) ? Xc[(size_t)f * ld + my_i] : 0.f;
+  }
+  if (RES) {
+    if (warp_ok)
+      for (int r = 0; r < R; ++r) {
+        long long q = 0;
+        if (my_ok) {
+          const float d = sqdist_reg_smem<CP>(xr, s_cand + (size_t)r * L * CP, C);
+          s_cl[r * kSeedThreads + threadIdx.x] = d;
+          q = to_fixed(d, sc.p_d);
+        }
+        q = warp_sum_q(q);
+        if (lane == 0) s_pot[(size_t)warp * RL + r * L] += q;
+      }
+  } else
   for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
     const int i = i0 + threadIdx.x;
     const bool ok = i < p_hi;
@@ -364,7 +398,7 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       // first range whose inclusive prefix reaches Tq: lo < Tq <= hi, or Tq <= 0 for the first range
       const bool mine = (p_lo < p_hi) && (hi >= Tq) && (b == 0 ? true : lo < Tq);
       if (mine) {
-        const float* __restrict__ cl = ws.closest + (size_t)r * ld;
+        const float* __restrict__ cl = RES ? (s_cl + r * kSeedThreads - p_lo) : (ws.closest + (size_t)r * ld);
         long long base = lo;
         for (int i0 = p_lo; i0 < p_hi; i0 += 32) {
           const int i = i0 + lane;
@@ -395,6 +429,19 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       s_cand[idx] = (f < C) ? Xc[(size_t)f * ld + s_cidx[pair]] : 0.f;
     }
     __syncthreads();
+    if (RES) {
+      if (warp_ok)
+        for (int r = 0; r < R; ++r) {
+          const float cl = my_ok ? s_cl[r * kSeedThreads + threadIdx.x] : 0.f;
+#pragma unroll 2
+          for (int t = 0; t < L; ++t) {
+            long long q = 0;
+            if (my_ok) q = to_fixed(fminf(cl, sqdist_reg_smem<CP>(xr, s_cand + (size_t)(r * L + t) * CP, C)), sc.p_d);
+            q = warp_sum_q(q);
+            if (lane == 0) s_pot[(size_t)warp * RL + r * L + t] = q;   // one chunk per CTA: plain store
+          }
+        }
+    } else
     for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
       const int i = i0 + threadIdx.x;
       const bool ok = i < p_hi;
@@ -435,6 +482,20 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
     }
     for (int idx = threadIdx.x; idx < NW * RL; idx += kSeedThreads) s_pot[idx] = 0;
     __syncthreads();
+    if (RES) {
+      if (warp_ok)
+        for (int r = 0; r < R; ++r) {
+          long long q = 0;
+          if (my_ok) {
+            float* cl = s_cl + r * kSeedThreads + threadIdx.x;
+            const float nd = fminf(*cl, sqdist_reg_smem<CP>(xr, s_cand + (size_t)(r * L + s_best[r]) * CP, C));
+            *cl = nd;
+            q = to_fixed(nd, sc.p_d);
+          }
+          q = warp_sum_q(q);
+          if (lane == 0) s_pot[(size_t)warp * RL + r * L] = q;
+        }
+    } else
     for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
       const int i = i0 + threadIdx.x;
       const bool ok = i < p_hi;
@@ -474,9 +535,10 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   }
 }
 
-size_t seed_smem_bytes(int R, int L, int CP) {
+size_t seed_smem_bytes(int R, int L, int CP, bool res) {
   const size_t RL = (size_t)R * L;
-  return RL * CP * 4 + (size_t)(kSeedThreads / 32) * RL * 8 + 3 * (size_t)R * 8 + RL * 8 + (size_t)R * 4 + RL * 4 + 16;
+  return RL * CP * 4 + (size_t)(kSeedThreads / 32) * RL * 8 + 3 * (size_t)R * 8 + RL * 8 + (size_t)R * 4 + (RL + 1) * 4 +
+         (res ? (size_t)R * kSeedThreads * 4 : 0) + 16;
 }
 
 // ------------------------------------------------------------------ Lloyd
@@ -939,23 +1001,48 @@ size_t lloyd_smem_bytes(int k, int C, int CP) {
   return fl * 4 + (size_t)kMaxTile * 4 + 16;
 }
 
-template <int CP>
-int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, int num_sms, cudaStream_t stream) {
-  const size_t smem = seed_smem_bytes(R, L, CP);
-  const void* fn = (const void*)km_seed_coop_kernel<CP>;
+template <int CP, bool RES>
+int launch_seed_v(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, int num_sms, cudaStream_t stream,
+                  bool* launched) {
+  const size_t smem = seed_smem_bytes(R, L, CP, RES);
+  const void* fn = (const void*)km_seed_coop_kernel<CP, RES>;
+  *launched = false;
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  if (smem > (size_t)di.max_smem_optin) {
+    ISA_CHECK_ARG(RES, "kmeans: seeding kernel needs %zu B of shared memory", smem);
+    return ISA_OK;   // resident variant does not fit: the caller falls back to the streaming variant
+  }
   if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSeedThreads, smem));
-  ISA_CHECK_ARG(occ >= 1, "kmeans: seeding kernel does not fit on an SM (smem %zu)", smem);
   if (occ > 2) occ = 2;
-  int grid = num_sms * occ;
-  const int want = (ld + 127) / 128;       // no point in CTAs with fewer than ~128 points
-  if (grid > want) grid = want;
-  if (grid > kSeedMaxCtas) grid = kSeedMaxCtas;
-  if (grid < 1) grid = 1;
+  int grid;
+  if (RES) {
+    grid = (ld + kSeedThreads - 1) / kSeedThreads;      // one point per thread
+    if (occ < 1 || grid > num_sms * occ || grid > kSeedMaxCtas) return ISA_OK;   // too many points to keep resident
+  } else {
+    ISA_CHECK_ARG(occ >= 1, "kmeans: seeding kernel does not fit on an SM (smem %zu)", smem);
+    grid = num_sms * occ;
+    const int want = (ld + 127) / 128;       // no point in CTAs with fewer than ~128 points
+    if (grid > want) grid = want;
+    if (grid > kSeedMaxCtas) grid = kSeedMaxCtas;
+    if (grid < 1) grid = 1;
+  }
   void* args[] = {(void*)&n_ptr, (void*)&ld, (void*)&C, (void*)&k, (void*)&L, (void*)&R, (void*)&uniforms, (void*)&ws};
   ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kSeedThreads), args, smem, stream));
+  *launched = true;
   return ISA_OK;
+}
+
+template <int CP>
+int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, int num_sms, cudaStream_t stream) {
+  bool launched = false;
+  int rc = ISA_OK;
+  if (!getenv("ISA_KM_STREAMING")) rc = launch_seed_v<CP, true>(n_ptr, ld, C, k, L, R, uniforms, ws, num_sms, stream, &launched);
+  if (rc || launched) return rc;
+  return launch_seed_v<CP, false>(n_ptr, ld, C, k, L, R, uniforms, ws, num_sms, stream, &launched);
 }
 
 template <int CP, int PPT>

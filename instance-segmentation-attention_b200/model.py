@@ -219,8 +219,9 @@ class Model(object):
         return history
 
     def __run_epoch(self, loader, clip_grad_norm, mode):
+        from .data import CudaPrefetcher
         sums, n = {}, 0
-        for images, sem, ins, nobj in loader:
+        for images, sem, ins, nobj in CudaPrefetcher(loader, self.device):
             m = self.train_step(images, sem, ins, nobj, clip_grad_norm, mode=mode)
             for k, v in m.items():
                 sums[k] = sums.get(k, 0.0) + v

@@ -80,6 +80,61 @@ class Prediction(object):
         res.check()
         return both[0].numpy(), both[1].numpy(), n
 
+    def predict_many(self, raw_images, prefetch=2):
+        """Pipelined `predict_array` over an iterable of HxWx3 uint8 images (what pred_list.py does with a list of
+        paths): a worker thread resizes / normalises / pins image i+1 (PIL releases the GIL) while the device works on
+        image i, and the masks of image i are copied back asynchronously while image i+1 is enqueued.
+        Yields (sem_seg uint8 HxW, ins_seg uint8 HxW, n_objects) in order; results are identical to predict_array."""
+        import queue
+        import threading
+        dev = self.model.device
+        q = queue.Queue(maxsize=max(1, int(prefetch)))
+
+        def producer():
+            try:
+                for raw in raw_images:
+                    image, h, w = self.image_to_tensor(raw)
+                    q.put((image.unsqueeze(0).pin_memory(), h, w))
+            finally:
+                q.put(None)
+
+        threading.Thread(target=producer, daemon=True).start()
+        n = self.model.n_objects_prediction
+        pending = None
+        ring = {}          # (h, w) -> two pinned staging buffers used alternately (masks + the k-means info words)
+        turn = 0
+        while True:
+            item = q.get()
+            if item is not None:
+                image, h, w = item
+                sem, emb = self.model.predict_device(image)
+                _, _, ins_up, cls_up, res = self.cluster_device(sem[0], emb[0], n, h, w)
+                bufs = ring.get((h, w))
+                if bufs is None:
+                    bufs = ring[(h, w)] = [(torch.empty(2, h, w, dtype=torch.uint8).pin_memory(),
+                                            torch.empty(16, dtype=torch.int32).pin_memory()) for _ in range(2)]
+                host, host_info = bufs[turn & 1]
+                turn += 1
+                host[0].copy_(cls_up, non_blocking=True)
+                host[1].copy_(ins_up, non_blocking=True)
+                host_info.copy_(res.info, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                cur = (host, host_info, ev)
+            else:
+                cur = None
+            if pending is not None:
+                host_p, info_p, ev_p = pending
+                ev_p.synchronize()
+                if int(info_p[0]) == 1:
+                    raise ValueError("n_samples=%d should be >= n_clusters." % int(info_p[2]))
+                if int(info_p[0]) == 2:
+                    raise ValueError("Input X contains NaN or infinity.")
+                yield host_p[0].numpy().copy(), host_p[1].numpy().copy(), n
+            if cur is None:
+                break
+            pending = cur
+
     def predict(self, image_path):
         raw_image = np.array(Image.open(image_path).convert('RGB'))
         if not self.model.use_instance_segmentation:

@@ -128,3 +128,19 @@ def same_up_to_permutation(a, b):
         return False
     pairs = np.unique(np.stack([a, b], 1), axis=0)
     return len(np.unique(pairs[:, 0])) == len(pairs) and len(np.unique(pairs[:, 1])) == len(pairs)
+
+
+def partition_agreement(a, b):
+    """Fraction of points on which label arrays a and b agree under the best one-to-one relabelling
+    (1.0 == same partition).  Used to QUANTIFY a mismatch against real scikit-learn, whose own fp32 sums are
+    not reproducible across BLAS builds / thread counts (near-tied restarts can then be ranked differently)."""
+    from scipy.optimize import linear_sum_assignment
+    a = np.asarray(a).ravel().astype(np.int64)
+    b = np.asarray(b).ravel().astype(np.int64)
+    ua, ia = np.unique(a, return_inverse=True)
+    ub, ib = np.unique(b, return_inverse=True)
+    cont = np.zeros((len(ua), len(ub)), dtype=np.int64)
+    np.add.at(cont, (ia, ib), 1)
+    r, c = linear_sum_assignment(-cont)
+    return float(cont[r, c].sum()) / max(len(a), 1)
+

@@ -143,3 +143,29 @@ def test_prediction_masks_bit_exact_and_sbd_identical(cuda, tmp_path):
     assert sem_t.shape == (1, 2, 64, 64) and ins_t.shape == (1, 24, 64, 64) and n_t.tolist() == [[5]]
     a, b, c = pred.cluster(sem_t[0], ins_t[0], n_t[0])
     assert a.dtype == np.uint8 and b.shape == (64, 64)
+
+
+def test_predict_many_equals_predict_array_and_prefetcher_is_lossless(cuda):
+    """The pipelined public paths (Prediction.predict_many, data.CudaPrefetcher) change scheduling, not results."""
+    from isa_b200 import synth
+    from isa_b200.data import CudaPrefetcher
+    from isa_b200.model import Model
+    from isa_b200.prediction import Prediction
+    from isa_b200.settings import CVPPPModelSettings
+    torch.manual_seed(3)
+    ms = CVPPPModelSettings()
+    model = Model('CVPPP', 'ReSeg', 2, 32, use_instance_segmentation=True, n_embedding=24, device=cuda)
+    pred = Prediction(64, 64, ms.MEAN, ms.STD, False, model, 1, seed=0, n_init=3)
+    model.n_objects_prediction = 4
+    raws = [synth.leaf_image(s, 90 + 7 * s, 80 + 5 * s) for s in range(4)]
+    many = list(pred.predict_many(iter(raws)))
+    assert len(many) == len(raws)
+    for raw, (sem, ins, n) in zip(raws, many):
+        sem1, ins1, n1 = pred.predict_array(raw)
+        assert n == n1 and np.array_equal(sem, sem1) and np.array_equal(ins, ins1)
+    batches = [(torch.randn(2, 3, 8, 8), torch.randint(0, 5, (2, 4), dtype=torch.int64), torch.tensor([1, 2])) for _ in range(5)]
+    got = list(CudaPrefetcher(batches, cuda))
+    assert len(got) == 5
+    for b, g in zip(batches, got):
+        for t, u in zip(b, g):
+            assert u.is_cuda and torch.equal(t, u.cpu())
