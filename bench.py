@@ -379,7 +379,7 @@ def run_ours(args):
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_reference(args.workload, steps=1, warmup=0)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -471,7 +471,30 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quarantine_stdout():
+    """Libraries print to fd 1 (NCCL's version banner, cuDNN notes): point fd 1 at stderr for the run and keep the
+    real stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
@@ -485,6 +508,7 @@ def main():
                     help="train workload: skip the extra pred.py inference leg reported under \"inference\" at N = 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _quarantine_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
