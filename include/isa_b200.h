@@ -37,6 +37,9 @@ int isa_num_sms(int* out);
 /* Diagnostics: mean device time (us) of one grid-wide barrier between ctas_per_sm * num_sms co-resident CTAs
  * (variant 0: fence per thread + sleeping poll, 1: cooperative-groups style) -- the fixed cost per iteration of the
  * persistent cooperative kernels.  Synchronises the device; scratch = 8 bytes of device memory; result on the host. */
+/* Diagnostics: FP32 multiply-adds per clock per SM sustained by scalar FFMA (packed = 0) or fma.rn.f32x2 / FFMA2
+ * (packed = 1) with warps_per_sm resident warps of 16 independent chains each; synchronises the device. */
+int isa_selftest_fma_rate(int packed, int warps_per_sm, float sm_clock_mhz, void* scratch, float* h_fma_per_clk_per_sm);
 int isa_selftest_grid_barrier(int ctas_per_sm, int threads, int iters, int variant, void* scratch, float* h_us_per_barrier);
 
 /* ------------------------------------------------------------------ discriminative loss
