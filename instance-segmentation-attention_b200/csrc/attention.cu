@@ -493,159 +493,68 @@ struct BwdParams {
   float inv_t;
 };
 
-// TMEM columns of both backward kernels: S [0,128), dP [128,256), accumulators from 256
+// ---- pipelined backward kernel (one template, two roles) -----------------------------------------------------------
+// The CTA owns one 128-row tile (DKDV = false: queries, produces dQ; DKDV = true: keys, produces dK and dV) and streams
+// the 128-wide tiles of the other side, each processed as two 64-column sub-tiles `u`:
+//   tensor pipe   S(u), dP(u) -> TMEM stage u&1 (6 MMAs, N = 64)          | all issued by one thread; S/dP of
+//                 acc += P/dA(u-1) x B  from shared stage (u-1)&1 (12/24 MMAs) | sub-tile u+1 overlap the math of u
+//   math warps    tcgen05.ld S, dP (stage freed at once) -> P = exp2(S - lse2), dA = P (dP - delta) -> bf16 hi/lo
+//                 K-major operand in shared stage u&1
+// so the exponentials of one sub-tile run while the tensor pipe works on its neighbours.  Tiles without masked
+// entries take a branch-free path (padded queries / keys contribute exact zeros through their zero operand rows).
+constexpr int kSub = 64;
+constexpr int kSubBytes = kTileQ * kSub * 2;          // one bf16 [128][64] operand: 16 KB
+constexpr int kSboSub = (kSub / 8) * 128;             // 1024
 constexpr int kTmS = 0, kTmDP = 128, kTmAcc0 = 256, kTmAcc1 = 272;
 
-struct DqSmem {
-  unsigned char q[2 * kOperandBytes];            // Q'h | Q'l
-  unsigned char go[2 * kOperandBytes];           // dOh | dOl
-  unsigned char kt[kStages][kBwdKTileBytes];     // Kh | Kl | Vh | Vl | K^T h | K^T l
-  unsigned char a_hi[kPBytes], a_lo[kPBytes];    // dA (A operand of dQ += dA K)
-  uint64_t c_full, s_full, a_full, o_full;
-  uint64_t kv_full[kStages], kv_empty[kStages];
+struct BwdSmem {
+  unsigned char own[4 * kOperandBytes];               // dQ: Q'h | Q'l | dOh | dOl      dK/dV: Kh | Kl | Vh | Vl
+  unsigned char oth[kStages][kBwdQTileBytes];         // streamed tiles of the other side (24 KB key / 33 KB query tiles)
+  unsigned char pa[2][4][kSubBytes];                  // [stage][P hi | P lo | dA hi | dA lo]
+  uint64_t c_full, o_full;
+  uint64_t s_full[2], s_free[2], a_full[2], pa_free[2];
+  uint64_t t_full[kStages], t_empty[kStages];
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const BwdParams prm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  DqSmem& sm = *reinterpret_cast<DqSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, bh = blockIdx.y;
-  const int nKt = prm.nKt;
-  const unsigned char* qtile = prm.qtiles + ((size_t)bh * prm.nQt + qt) * kBwdQTileBytes;
-  if (threadIdx.x == 0) {
-    mbar_init(&sm.c_full, 1); mbar_init(&sm.s_full, 1); mbar_init(&sm.a_full, 256); mbar_init(&sm.o_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm.tmem_base;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&sm.c_full, 4 * kOperandBytes);
-      tma_bulk_g2s(sm.q, qtile, 2 * kOperandBytes, &sm.c_full);
-      tma_bulk_g2s(sm.go, qtile + 4 * kOperandBytes, 2 * kOperandBytes, &sm.c_full);
-      for (int j = 0; j < nKt; ++j) {
-        const int st = j % kStages;
-        mbar_wait(&sm.kv_empty[st], ((j / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&sm.kv_full[st], kBwdKTileBytes);
-        tma_bulk_g2s(sm.kt[st], prm.ktiles + ((size_t)bh * nKt + j) * kBwdKTileBytes, kBwdKTileBytes, &sm.kv_full[st]);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(128, 128);
-      constexpr uint32_t idesc_o = make_idesc(128, kDP);
-      const uint32_t q_hi = smem_u32(sm.q), q_lo = q_hi + kOperandBytes;
-      const uint32_t g_hi = smem_u32(sm.go), g_lo = g_hi + kOperandBytes;
-      const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
-      mbar_wait(&sm.c_full, 0);
-      for (int j = 0; j < nKt; ++j) {
-        const int st = j % kStages;
-        const uint32_t kb = smem_u32(sm.kt[st]);
-        const uint32_t k_hi = kb, k_lo = kb + kOperandBytes, v_hi = kb + 2 * kOperandBytes, v_lo = kb + 3 * kOperandBytes;
-        const uint32_t kt_hi = kb + 4 * kOperandBytes, kt_lo = kb + 5 * kOperandBytes;
-        mbar_wait(&sm.kv_full[st], (j / kStages) & 1);
-        tc_fence_after();
-        // S = Q' K^T ; dP = dO V^T
-        umma_bf16(tmem + kTmS, make_desc(q_hi, 128, kSboQK), make_desc(k_hi, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tmem + kTmS, make_desc(q_hi, 128, kSboQK), make_desc(k_lo, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem + kTmS, make_desc(q_lo, 128, kSboQK), make_desc(k_hi, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem + kTmDP, make_desc(g_hi, 128, kSboQK), make_desc(v_hi, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tmem + kTmDP, make_desc(g_hi, 128, kSboQK), make_desc(v_lo, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem + kTmDP, make_desc(g_lo, 128, kSboQK), make_desc(v_hi, 128, kSboQK), idesc_s, 1);
-        umma_commit(&sm.s_full);
-        mbar_wait(&sm.a_full, j & 1);
-        tc_fence_after();
-        // dQ += dA K   (B = K^T tile)
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t ko = kk * 256;
-          umma_bf16(tmem + kTmAcc0, make_desc(a_hi + ko, 128, kSboP), make_desc(kt_hi + ko, 128, kSboP), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-          umma_bf16(tmem + kTmAcc0, make_desc(a_hi + ko, 128, kSboP), make_desc(kt_lo + ko, 128, kSboP), idesc_o, 1);
-          umma_bf16(tmem + kTmAcc0, make_desc(a_lo + ko, 128, kSboP), make_desc(kt_hi + ko, 128, kSboP), idesc_o, 1);
-        }
-        umma_commit(&sm.kv_empty[st]);
-      }
-      umma_commit(&sm.o_full);
-    }
-  } else {
-    // 8 math warps: (TMEM quarter = warp % 4, column half = (warp - 2) / 4)
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const int r = quarter * 32 + lane;
-    const int row = qt * kTileQ + r;
-    const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-    const float* stats = reinterpret_cast<const float*>(qtile + 8 * kOperandBytes);
-    const float l2 = __ldg(stats + r), dl = __ldg(stats + kTileQ + r);
-    for (int j = 0; j < nKt; ++j) {
-      const int key0 = j * kTileK;
-      const bool masked = tile_needs_mask(prm.mask, bh, prm.Lk, key0, lane);
-      uint32_t bits[4] = {0u, 0u, 0u, 0u};
-      if (masked) key_bits(prm.mask, bh, row, prm.Lq, prm.Lk, key0, bits);
-      mbar_wait(&sm.s_full, j & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        float s[32], dp[32];
-        tmem_ld32(t_row + kTmS + c * 32, s);
-        tmem_ld32(t_row + kTmDP + c * 32, dp);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float a[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int i = g * 8 + e;
-            float p = ex2_approx(s[i] - l2);
-            if (masked && ((bits[c] >> i) & 1u)) p = 0.f;
-            a[e] = p * (dp[i] - dl);
-          }
-          store_group(sm.a_hi, sm.a_lo, kmajor_off(r, c * 32 + g * 8, kSboP), a);
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&sm.a_full);
-    }
-    mbar_wait(&sm.o_full, 0);
-    tc_fence_after();
-    if (half == 0) {
-      float o[16];
-      tmem_ld16(t_row + kTmAcc0, o);
-      if (row < prm.Lq) {
-        float* dst = prm.dq + ((size_t)bh * prm.Lq + row) * prm.d;
-        for (int i = 0; i < prm.d; ++i) dst[i] = o[i] * prm.inv_t;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, kBwdTmemCols);
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// tcgen05.wait::ld that also names the loaded registers, so no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
-struct DkvSmem {
-  unsigned char kv[4 * kOperandBytes];                       // Kh | Kl | Vh | Vl   (this CTA's key tile)
-  unsigned char qt[kStages][kBwdQTileBytes];                 // per query tile (33 KB)
-  unsigned char p_hi[kPBytes], p_lo[kPBytes];                // P^T
-  unsigned char a_hi[kPBytes], a_lo[kPBytes];                // dA^T
-  uint64_t c_full, s_full, a_full, o_full;
-  uint64_t q_full[kStages], q_empty[kStages];
-  uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const BwdParams prm) {
+template <bool DKDV>
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  DkvSmem& sm = *reinterpret_cast<DkvSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, bh = blockIdx.y;
-  const int nQt = prm.nQt;
+  const int own_t = blockIdx.x, bh = blockIdx.y;
+  const int nT = DKDV ? prm.nQt : prm.nKt;            // streamed tiles
+  const int U = 2 * nT;                               // sub-tiles
+  constexpr uint32_t kOthBytes = DKDV ? kBwdQTileBytes : kBwdKTileBytes;
+  const unsigned char* own_src = DKDV ? prm.ktiles + ((size_t)bh * prm.nKt + own_t) * kBwdKTileBytes
+                                      : prm.qtiles + ((size_t)bh * prm.nQt + own_t) * kBwdQTileBytes;
+  const unsigned char* oth_src = DKDV ? prm.qtiles + (size_t)bh * prm.nQt * kBwdQTileBytes : prm.ktiles + (size_t)bh * prm.nKt * kBwdKTileBytes;
+
   if (threadIdx.x == 0) {
-    mbar_init(&sm.c_full, 1); mbar_init(&sm.s_full, 1); mbar_init(&sm.a_full, 256); mbar_init(&sm.o_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1); }
+    mbar_init(&sm.c_full, 1); mbar_init(&sm.o_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.s_full[s], 1); mbar_init(&sm.s_free[s], 256); mbar_init(&sm.a_full[s], 256); mbar_init(&sm.pa_free[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.t_full[s], 1); mbar_init(&sm.t_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
@@ -655,117 +564,206 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const Bwd
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == 0) {
+    // ===================== producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(&sm.c_full, 4 * kOperandBytes);
-      tma_bulk_g2s(sm.kv, prm.ktiles + ((size_t)bh * prm.nKt + kt) * kBwdKTileBytes, 4 * kOperandBytes, &sm.c_full);
-      for (int i = 0; i < nQt; ++i) {
+      if (DKDV) {
+        tma_bulk_g2s(sm.own, own_src, 4 * kOperandBytes, &sm.c_full);                              // Kh | Kl | Vh | Vl
+      } else {
+        tma_bulk_g2s(sm.own, own_src, 2 * kOperandBytes, &sm.c_full);                              // Q'h | Q'l
+        tma_bulk_g2s(sm.own + 2 * kOperandBytes, own_src + 4 * kOperandBytes, 2 * kOperandBytes, &sm.c_full);   // dOh | dOl
+      }
+      for (int i = 0; i < nT; ++i) {
         const int st = i % kStages;
-        mbar_wait(&sm.q_empty[st], ((i / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&sm.q_full[st], kBwdQTileBytes);
-        tma_bulk_g2s(sm.qt[st], prm.qtiles + ((size_t)bh * nQt + i) * kBwdQTileBytes, kBwdQTileBytes, &sm.q_full[st]);
+        mbar_wait(&sm.t_empty[st], ((i / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&sm.t_full[st], kOthBytes);
+        tma_bulk_g2s(sm.oth[st], oth_src + (size_t)i * kOthBytes, kOthBytes, &sm.t_full[st]);
       }
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(128, 128);
+      constexpr uint32_t idesc_s = make_idesc(128, kSub);
       constexpr uint32_t idesc_o = make_idesc(128, kDP);
-      const uint32_t k_hi = smem_u32(sm.kv), k_lo = k_hi + kOperandBytes, v_hi = k_hi + 2 * kOperandBytes, v_lo = k_hi + 3 * kOperandBytes;
-      const uint32_t p_hi = smem_u32(sm.p_hi), p_lo = smem_u32(sm.p_lo), a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
-      mbar_wait(&sm.c_full, 0);
-      for (int i = 0; i < nQt; ++i) {
-        const int st = i % kStages;
-        const uint32_t qb = smem_u32(sm.qt[st]);
-        const uint32_t q_hi = qb, q_lo = qb + kOperandBytes, qT_hi = qb + 2 * kOperandBytes, qT_lo = qb + 3 * kOperandBytes;
-        const uint32_t g_hi = qb + 4 * kOperandBytes, g_lo = qb + 5 * kOperandBytes, gT_hi = qb + 6 * kOperandBytes, gT_lo = qb + 7 * kOperandBytes;
-        mbar_wait(&sm.q_full[st], (i / kStages) & 1);
+      const uint32_t a0_hi = smem_u32(sm.own), a0_lo = a0_hi + kOperandBytes;                      // A of S:  Q' (dQ) / K (dK,dV)
+      const uint32_t a1_hi = a0_hi + 2 * kOperandBytes, a1_lo = a0_hi + 3 * kOperandBytes;         // A of dP: dO (dQ) / V (dK,dV)
+      // byte offsets inside a streamed tile: B of S, B of dP (row operands), B of the accumulations (transposed operands)
+      constexpr uint32_t oS = 0, oP = DKDV ? 4 * kOperandBytes : 2 * kOperandBytes;
+      constexpr uint32_t oB0 = DKDV ? 6 * kOperandBytes : 4 * kOperandBytes;                       // dO^T (dV) / K^T (dQ)
+      constexpr uint32_t oB1 = 2 * kOperandBytes;                                                  // Q'^T (dK)
+      auto accumulate = [&](int v) {
+        const int b = v & 1;
+        const uint32_t ob = smem_u32(sm.oth[(v >> 1) % kStages]) + (uint32_t)(v & 1) * 1024u;      // 64 k = 8 core matrices of 128 B
+        const uint32_t pa = smem_u32(sm.pa[b][0]);
+        mbar_wait(&sm.a_full[b], (v >> 1) & 1);
         tc_fence_after();
-        // S^T = K Q'^T ; dP^T = V dO^T   (rows = keys, columns = queries)
-        umma_bf16(tmem + kTmS, make_desc(k_hi, 128, kSboQK), make_desc(q_hi, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tmem + kTmS, make_desc(k_hi, 128, kSboQK), make_desc(q_lo, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem + kTmS, make_desc(k_lo, 128, kSboQK), make_desc(q_hi, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem + kTmDP, make_desc(v_hi, 128, kSboQK), make_desc(g_hi, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tmem + kTmDP, make_desc(v_hi, 128, kSboQK), make_desc(g_lo, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem + kTmDP, make_desc(v_lo, 128, kSboQK), make_desc(g_hi, 128, kSboQK), idesc_s, 1);
-        umma_commit(&sm.s_full);
-        mbar_wait(&sm.a_full, i & 1);
-        tc_fence_after();
-        // dV += P^T dO (B = dO^T tile) ; dK += dA^T Q' (B = Q'^T tile)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < kSub / 16; ++kk) {
           const uint32_t ko = kk * 256;
-          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
-          umma_bf16(tmem + kTmAcc0, make_desc(p_hi + ko, 128, kSboP), make_desc(gT_hi + ko, 128, kSboP), idesc_o, acc);
-          umma_bf16(tmem + kTmAcc0, make_desc(p_hi + ko, 128, kSboP), make_desc(gT_lo + ko, 128, kSboP), idesc_o, 1);
-          umma_bf16(tmem + kTmAcc0, make_desc(p_lo + ko, 128, kSboP), make_desc(gT_hi + ko, 128, kSboP), idesc_o, 1);
-          umma_bf16(tmem + kTmAcc1, make_desc(a_hi + ko, 128, kSboP), make_desc(qT_hi + ko, 128, kSboP), idesc_o, acc);
-          umma_bf16(tmem + kTmAcc1, make_desc(a_hi + ko, 128, kSboP), make_desc(qT_lo + ko, 128, kSboP), idesc_o, 1);
-          umma_bf16(tmem + kTmAcc1, make_desc(a_lo + ko, 128, kSboP), make_desc(qT_hi + ko, 128, kSboP), idesc_o, 1);
+          const uint32_t acc = (v > 0 || kk > 0) ? 1u : 0u;
+          if (DKDV) {
+            umma_bf16(tmem + kTmAcc0, make_desc(pa + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
+            umma_bf16(tmem + kTmAcc0, make_desc(pa + ko, 128, kSboSub), make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16(tmem + kTmAcc0, make_desc(pa + kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16(tmem + kTmAcc1, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, acc);
+            umma_bf16(tmem + kTmAcc1, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB1 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16(tmem + kTmAcc1, make_desc(pa + 3 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, 1);
+          } else {
+            umma_bf16(tmem + kTmAcc0, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
+            umma_bf16(tmem + kTmAcc0, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16(tmem + kTmAcc0, make_desc(pa + 3 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
+          }
         }
-        umma_commit(&sm.q_empty[st]);
+        umma_commit(&sm.pa_free[b]);
+        if (v & 1) umma_commit(&sm.t_empty[(v >> 1) % kStages]);
+      };
+      mbar_wait(&sm.c_full, 0);
+      for (int u = 0; u < U; ++u) {
+        const int b = u & 1, n = u >> 1, st = n % kStages;
+        if (b == 0) mbar_wait(&sm.t_full[st], (n / kStages) & 1);
+        if (n >= 1) mbar_wait(&sm.s_free[b], (n - 1) & 1);
+        tc_fence_after();
+        const uint32_t ob = smem_u32(sm.oth[st]) + (uint32_t)b * 2048u;                            // 64 rows = 8 row groups of 256 B
+        const uint32_t tS = tmem + kTmS + b * kSub, tP = tmem + kTmDP + b * kSub;
+        umma_bf16(tS, make_desc(a0_hi, 128, kSboQK), make_desc(ob + oS, 128, kSboQK), idesc_s, 0);
+        umma_bf16(tS, make_desc(a0_hi, 128, kSboQK), make_desc(ob + oS + kOperandBytes, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tS, make_desc(a0_lo, 128, kSboQK), make_desc(ob + oS, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tP, make_desc(a1_hi, 128, kSboQK), make_desc(ob + oP, 128, kSboQK), idesc_s, 0);
+        umma_bf16(tP, make_desc(a1_hi, 128, kSboQK), make_desc(ob + oP + kOperandBytes, 128, kSboQK), idesc_s, 1);
+        umma_bf16(tP, make_desc(a1_lo, 128, kSboQK), make_desc(ob + oP, 128, kSboQK), idesc_s, 1);
+        umma_commit(&sm.s_full[b]);
+        if (u >= 1) accumulate(u - 1);
       }
+      accumulate(U - 1);
       umma_commit(&sm.o_full);
     }
   } else {
+    // ===================== 8 math warps: TMEM quarter = warp % 4, 32-column half = (warp - 2) / 4 =====================
     const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const int r = quarter * 32 + lane;            // key row inside the tile
-    const int key = kt * kTileK + r;
+    const int r = quarter * 32 + lane;                  // row inside the own tile
+    const int own_row = own_t * 128 + r;
     const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-    bool row_masked = key >= prm.Lk;
-    if (!row_masked && prm.mask.key_mask) row_masked = prm.mask.key_mask[(size_t)(bh % prm.mask.n_mask_rows) * prm.Lk + key] != 0;
-    const unsigned char* fm = prm.mask.full_mask ? prm.mask.full_mask + (size_t)(bh % prm.mask.n_mask_rows) * prm.Lq * prm.Lk : nullptr;
-    for (int i = 0; i < nQt; ++i) {
-      const int st = i % kStages;
-      const int q0 = i * kTileQ;
-      mbar_wait(&sm.q_full[st], (i / kStages) & 1);     // lse2 / delta of this query tile are in smem
-      const float* stats = reinterpret_cast<const float*>(sm.qt[st] + 8 * kOperandBytes);
-      mbar_wait(&sm.s_full, i & 1);
+    // per-row constants
+    float l2_row = 0.f, dl_row = 0.f;
+    bool row_masked = false;
+    const unsigned char* fm = nullptr;
+    bool slow_rows = false;
+    if (DKDV) {
+      row_masked = own_row >= prm.Lk;
+      if (!row_masked && prm.mask.key_mask) row_masked = prm.mask.key_mask[(size_t)(bh % prm.mask.n_mask_rows) * prm.Lk + own_row] != 0;
+      fm = prm.mask.full_mask ? prm.mask.full_mask + (size_t)(bh % prm.mask.n_mask_rows) * prm.Lq * prm.Lk : nullptr;
+      // padded rows (own_row >= Lk) may stay on the fast path: their outputs are never stored
+      slow_rows = __any_sync(0xffffffffu, row_masked && own_row < prm.Lk) || fm != nullptr;
+    } else {
+      const float* stats = reinterpret_cast<const float*>(own_src + 8 * kOperandBytes);
+      l2_row = __ldg(stats + r);
+      dl_row = __ldg(stats + kTileQ + r);
+    }
+    uint32_t bits[4] = {0u, 0u, 0u, 0u};
+    bool masked = DKDV ? slow_rows : false;
+    for (int u = 0; u < U; ++u) {
+      const int b = u & 1, n = u >> 1, st = n % kStages;
+      const int col0 = b * kSub + half * 32;             // first column (inside the streamed 128-tile) of this thread's 32
+      if (!DKDV && b == 0) {
+        masked = tile_needs_mask(prm.mask, bh, prm.Lk, n * kTileK, lane);
+        if (masked) key_bits(prm.mask, bh, own_row, prm.Lq, prm.Lk, n * kTileK, bits);
+      }
+      if (DKDV && b == 0) mbar_wait(&sm.t_full[st], (n / kStages) & 1);     // lse2 / delta of this query tile are in smem
+      mbar_wait(&sm.s_full[b], n & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        float s[32], dp[32];
-        tmem_ld32(t_row + kTmS + c * 32, s);
-        tmem_ld32(t_row + kTmDP + c * 32, dp);
+      uint32_t sr[32], dr[32];
+      tmem_ld32_issue(t_row + kTmS + b * kSub + half * 32, sr);
+      tmem_ld32_issue(t_row + kTmDP + b * kSub + half * 32, dr);
+      tmem_ld32_wait(sr);
+      tmem_ld32_wait(dr);
+      tc_fence_before();
+      mbar_arrive(&sm.s_free[b]);                         // the TMEM stage may be overwritten by sub-tile u + 2
+      if (n >= 1) mbar_wait(&sm.pa_free[b], (n - 1) & 1);  // the MMAs of sub-tile u - 2 have consumed this shared stage
+      unsigned char* p_hi = sm.pa[b][0];
+      unsigned char* p_lo = sm.pa[b][1];
+      unsigned char* a_hi = sm.pa[b][2];
+      unsigned char* a_lo = sm.pa[b][3];
+      const float* stats = reinterpret_cast<const float*>(sm.oth[st] + 8 * kOperandBytes);
+      if (!masked) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float p8[8], a8[8];
-          const float4 l2a = *reinterpret_cast<const float4*>(stats + c * 32 + g * 8);
-          const float4 l2b = *reinterpret_cast<const float4*>(stats + c * 32 + g * 8 + 4);
-          const float4 dla = *reinterpret_cast<const float4*>(stats + kTileQ + c * 32 + g * 8);
-          const float4 dlb = *reinterpret_cast<const float4*>(stats + kTileQ + c * 32 + g * 8 + 4);
-          const float l2v[8] = {l2a.x, l2a.y, l2a.z, l2a.w, l2b.x, l2b.y, l2b.z, l2b.w};
-          const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
+          if (DKDV) {
+            const float4 l2a = *reinterpret_cast<const float4*>(stats + col0 + g * 8);
+            const float4 l2b = *reinterpret_cast<const float4*>(stats + col0 + g * 8 + 4);
+            const float4 dla = *reinterpret_cast<const float4*>(stats + kTileQ + col0 + g * 8);
+            const float4 dlb = *reinterpret_cast<const float4*>(stats + kTileQ + col0 + g * 8 + 4);
+            const float l2v[8] = {l2a.x, l2a.y, l2a.z, l2a.w, l2b.x, l2b.y, l2b.z, l2b.w};
+            const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float p = ex2_approx(__uint_as_float(sr[g * 8 + e]) - l2v[e]);
+              p8[e] = p;
+              a8[e] = p * (__uint_as_float(dr[g * 8 + e]) - dlv[e]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float p = ex2_approx(__uint_as_float(sr[g * 8 + e]) - l2_row);
+              a8[e] = p * (__uint_as_float(dr[g * 8 + e]) - dl_row);
+            }
+          }
+          const int off = kmajor_off(r, half * 32 + g * 8, kSboSub);
+          if (DKDV) store_group(p_hi, p_lo, off, p8);
+          store_group(a_hi, a_lo, off, a8);
+        }
+      } else {
+        const uint32_t mbits = b ? (half ? bits[3] : bits[2]) : (half ? bits[1] : bits[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float p8[8], a8[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int ii = g * 8 + e;
-            const int qi = q0 + c * 32 + ii;
-            float p = ex2_approx(s[ii] - l2v[e]);
-            bool mk = row_masked || qi >= prm.Lq;
-            if (fm && !mk) mk = fm[(size_t)qi * prm.Lk + key] != 0;
+            const int i = g * 8 + e;
+            float l2 = l2_row, dl = dl_row;
+            bool mk;
+            if (DKDV) {
+              const int qi = n * kTileQ + col0 + i;
+              l2 = stats[col0 + i];
+              dl = stats[kTileQ + col0 + i];
+              mk = row_masked || qi >= prm.Lq;
+              if (fm && !mk) mk = fm[(size_t)qi * prm.Lk + own_row] != 0;
+            } else {
+              mk = (mbits >> i) & 1u;
+            }
+            float p = ex2_approx(__uint_as_float(sr[i]) - l2);
             if (mk) p = 0.f;
             p8[e] = p;
-            a8[e] = p * (dp[ii] - dlv[e]);
+            a8[e] = p * (__uint_as_float(dr[i]) - dl);
           }
-          const int off = kmajor_off(r, c * 32 + g * 8, kSboP);
-          store_group(sm.p_hi, sm.p_lo, off, p8);
-          store_group(sm.a_hi, sm.a_lo, off, a8);
+          const int off = kmajor_off(r, half * 32 + g * 8, kSboSub);
+          if (DKDV) store_group(p_hi, p_lo, off, p8);
+          store_group(a_hi, a_lo, off, a8);
         }
       }
       fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&sm.a_full);
+      mbar_arrive(&sm.a_full[b]);
     }
     mbar_wait(&sm.o_full, 0);
     tc_fence_after();
-    float o[16];
-    tmem_ld16(t_row + (half == 0 ? kTmAcc0 : kTmAcc1), o);
-    if (key < prm.Lk) {
-      if (half == 0) {
-        float* dst = prm.dv + ((size_t)bh * prm.Lk + key) * prm.dv_dim;
-        for (int c = 0; c < prm.dv_dim; ++c) dst[c] = o[c];
-      } else {
-        float* dst = prm.dk + ((size_t)bh * prm.Lk + key) * prm.d;
-        for (int c = 0; c < prm.d; ++c) dst[c] = o[c] * 0.6931471805599453f;   // ln 2: S was in the exp2 domain
+    if (DKDV) {
+      float o[16];
+      tmem_ld16(t_row + (half == 0 ? kTmAcc0 : kTmAcc1), o);
+      if (own_row < prm.Lk) {
+        if (half == 0) {
+          float* dst = prm.dv + ((size_t)bh * prm.Lk + own_row) * prm.dv_dim;
+          for (int c = 0; c < prm.dv_dim; ++c) dst[c] = o[c];
+        } else {
+          float* dst = prm.dk + ((size_t)bh * prm.Lk + own_row) * prm.d;
+          for (int c = 0; c < prm.d; ++c) dst[c] = o[c] * 0.6931471805599453f;   // ln 2: S was in the exp2 domain
+        }
+      }
+    } else if (half == 0) {
+      float o[16];
+      tmem_ld16(t_row + kTmAcc0, o);
+      if (own_row < prm.Lq) {
+        float* dst = prm.dq + ((size_t)bh * prm.Lq + own_row) * prm.d;
+        for (int i = 0; i < prm.d; ++i) dst[i] = o[i] * prm.inv_t;
       }
     }
   }
@@ -879,11 +877,11 @@ int isa_attention_bwd(const float* q, const float* k, const float* v, const floa
   bp.mask.key_mask = key_mask; bp.mask.full_mask = full_mask; bp.mask.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
   bp.dq = dq; bp.dk = dk; bp.dv = dvv; bp.BH = BH; bp.Lq = Lq; bp.Lk = Lk; bp.d = d; bp.dv_dim = dv; bp.nQt = nQt; bp.nKt = nKt;
   bp.inv_t = 1.f / temperature;
-  const size_t smem_dq = sizeof(DqSmem) + 1024, smem_dkv = sizeof(DkvSmem) + 1024;
-  ISA_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
-  ISA_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv));
-  attn_bwd_dq_kernel<<<dim3(nQt, BH), kBwdThreads, smem_dq, stream>>>(bp);
-  attn_bwd_dkdv_kernel<<<dim3(nKt, BH), kBwdThreads, smem_dkv, stream>>>(bp);
+  const size_t smem = sizeof(BwdSmem) + 1024;
+  ISA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_bwd_kernel<false><<<dim3(nQt, BH), kBwdThreads, smem, stream>>>(bp);   // dQ
+  attn_bwd_kernel<true><<<dim3(nKt, BH), kBwdThreads, smem, stream>>>(bp);    // dK, dV
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }
