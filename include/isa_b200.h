@@ -40,6 +40,8 @@ int isa_num_sms(int* out);
 /* Diagnostics: FP32 multiply-adds per clock per SM sustained by scalar FFMA (packed = 0) or fma.rn.f32x2 / FFMA2
  * (packed = 1) with warps_per_sm resident warps of 16 independent chains each; synchronises the device. */
 int isa_selftest_fma_rate(int packed, int warps_per_sm, float sm_clock_mhz, void* scratch, float* h_fma_per_clk_per_sm);
+/* Diagnostics: TMEM read rate (bytes per clock per SM) of `warps` in {4,8,16} warps issuing tcgen05.ld.32x32b.x{cols}, cols in {16,32}. */
+int isa_selftest_tmem_ld_rate(int warps, int cols, float sm_clock_mhz, void* scratch, float* h_bytes_per_clk_per_sm);
 int isa_selftest_grid_barrier(int ctas_per_sm, int threads, int iters, int variant, void* scratch, float* h_us_per_barrier);
 
 /* ------------------------------------------------------------------ discriminative loss

@@ -28,6 +28,7 @@ SIGNATURES = {
     "isa_version": (c_int, []),
     "isa_num_sms": (c_int, [ctypes.POINTER(c_int)]),
     "isa_selftest_fma_rate": (c_int, [c_int, c_int, c_float, c_void_p, ctypes.POINTER(c_float)]),
+    "isa_selftest_tmem_ld_rate": (c_int, [c_int, c_int, c_float, c_void_p, ctypes.POINTER(c_float)]),
     "isa_selftest_grid_barrier": (c_int, [c_int, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_float)]),
     # discriminative loss
     "isa_disc_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -495,25 +495,26 @@ struct BwdParams {
 
 // ---- pipelined backward kernel (one template, two roles) -----------------------------------------------------------
 // The CTA owns one 128-row tile (DKDV = false: queries, produces dQ; DKDV = true: keys, produces dK and dV) and streams
-// the 128-wide tiles of the other side, each processed as two 64-column sub-tiles `u`:
-//   tensor pipe   S(u), dP(u) -> TMEM stage u&1 (6 MMAs, N = 64)          | all issued by one thread; S/dP of
-//                 acc += P/dA(u-1) x B  from shared stage (u-1)&1 (12/24 MMAs) | sub-tile u+1 overlap the math of u
-//   math warps    tcgen05.ld S, dP (stage freed at once) -> P = exp2(S - lse2), dA = P (dP - delta) -> bf16 hi/lo
-//                 K-major operand in shared stage u&1
-// so the exponentials of one sub-tile run while the tensor pipe works on its neighbours.  Tiles without masked
-// entries take a branch-free path (padded queries / keys contribute exact zeros through their zero operand rows).
+// the 128-wide tiles of the other side, each processed as two 64-column sub-tiles `u`.  TMEM stage u&1 (128 columns):
+//   tensor pipe   S(u) -> cols [0,64), dP(u) -> cols [64,128)                     (6 MMAs, N = 64, operands in smem)
+//   math warps    tcgen05.ld S, dP -> P = exp2(S - lse2), dA = P (dP - delta) -> bf16 hi/lo pairs written back with
+//                 tcgen05.st OVER the S/dP columns the same thread has just read (P over S, dA over dP)
+//   tensor pipe   acc += P/dA(u) x B  with the A operand read from TMEM (12 / 24 MMAs, N = 16), then S, dP(u+2)
+// so the exponentials of sub-tile u+1 run while the tensor pipe works on u and u+2, and P/dA never touch shared memory
+// (the shared-memory version spent more than half of the SM's smem bandwidth on 16 KB operand re-reads by N = 16 MMAs).
+// Tiles without masked entries take a branch-free path (padded queries / keys contribute exact zeros through their
+// zero operand rows).
 constexpr int kSub = 64;
-constexpr int kSubBytes = kTileQ * kSub * 2;          // one bf16 [128][64] operand: 16 KB
-constexpr int kSboSub = (kSub / 8) * 128;             // 1024
-constexpr int kTmS = 0, kTmDP = 128, kTmAcc0 = 256, kTmAcc1 = 272;
+constexpr int kBwdStages = 3;
+constexpr int kTmStage = 128;                           // TMEM columns per stage: S | dP
+constexpr int kTmAcc0 = 256, kTmAcc1 = 272;
 
 struct BwdSmem {
-  unsigned char own[4 * kOperandBytes];               // dQ: Q'h | Q'l | dOh | dOl      dK/dV: Kh | Kl | Vh | Vl
-  unsigned char oth[kStages][kBwdQTileBytes];         // streamed tiles of the other side (24 KB key / 33 KB query tiles)
-  unsigned char pa[2][4][kSubBytes];                  // [stage][P hi | P lo | dA hi | dA lo]
+  unsigned char own[4 * kOperandBytes];                 // dQ: Q'h | Q'l | dOh | dOl      dK/dV: Kh | Kl | Vh | Vl
+  unsigned char oth[kBwdStages][kBwdQTileBytes];        // streamed tiles of the other side (24 KB key / 33 KB query tiles)
   uint64_t c_full, o_full;
-  uint64_t s_full[2], s_free[2], a_full[2], pa_free[2];
-  uint64_t t_full[kStages], t_empty[kStages];
+  uint64_t s_full[2], a_full[2];
+  uint64_t t_full[kBwdStages], t_empty[kBwdStages];
   uint32_t tmem_base;
 };
 
@@ -537,6 +538,71 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16_issue(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+               "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is M x 16 bf16 held as 8 columns of packed pairs (row = lane)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct BwdMaskCtx {           // per-thread mask state of the slow path
+  uint32_t bits;              // dQ: masked keys among this thread's 32 columns
+  bool row_masked;            // dK/dV: this key is masked for every query
+  const unsigned char* fm;    // dK/dV: full mask base for this head (or null)
+  int q0, Lq, Lk, own_row;
+};
+
+// one thread, 32 columns: registers of S and dP -> packed bf16 hi/lo pairs of P and dA
+template <bool DKDV, bool MASKED>
+__device__ __forceinline__ void bwd_math(const uint32_t (&sr)[32], const uint32_t (&dr)[32], const float* __restrict__ st_l2, const float* __restrict__ st_dl,
+                                         float l2_row, float dl_row, const BwdMaskCtx& mc, uint32_t (&ph)[16], uint32_t (&pl)[16], uint32_t (&ah)[16],
+                                         uint32_t (&al)[16]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float l2v[4] = {l2_row, l2_row, l2_row, l2_row}, dlv[4] = {dl_row, dl_row, dl_row, dl_row};
+    if (DKDV) {
+      const float4 a = *reinterpret_cast<const float4*>(st_l2 + g * 4);
+      const float4 d = *reinterpret_cast<const float4*>(st_dl + g * 4);
+      l2v[0] = a.x; l2v[1] = a.y; l2v[2] = a.z; l2v[3] = a.w;
+      dlv[0] = d.x; dlv[1] = d.y; dlv[2] = d.z; dlv[3] = d.w;
+    }
+    float p4[4], a4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = g * 4 + e;
+      float p = ex2_approx(__uint_as_float(sr[i]) - l2v[e]);
+      if (MASKED) {
+        bool mk;
+        if (DKDV) {
+          const int qi = mc.q0 + i;
+          mk = mc.row_masked || qi >= mc.Lq;
+          if (mc.fm && !mk) mk = mc.fm[(size_t)qi * mc.Lk + mc.own_row] != 0;
+        } else {
+          mk = (mc.bits >> i) & 1u;
+        }
+        if (mk) p = 0.f;
+      }
+      p4[e] = p;
+      a4[e] = p * (__uint_as_float(dr[i]) - dlv[e]);
+    }
+    if (DKDV) {
+      split2(p4[0], p4[1], ph[g * 2], pl[g * 2]);
+      split2(p4[2], p4[3], ph[g * 2 + 1], pl[g * 2 + 1]);
+    }
+    split2(a4[0], a4[1], ah[g * 2], al[g * 2]);
+    split2(a4[2], a4[3], ah[g * 2 + 1], al[g * 2 + 1]);
+  }
+}
 
 template <bool DKDV>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParams prm) {
@@ -553,8 +619,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
 
   if (threadIdx.x == 0) {
     mbar_init(&sm.c_full, 1); mbar_init(&sm.o_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&sm.s_full[s], 1); mbar_init(&sm.s_free[s], 256); mbar_init(&sm.a_full[s], 256); mbar_init(&sm.pa_free[s], 1); }
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.t_full[s], 1); mbar_init(&sm.t_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.s_full[s], 1); mbar_init(&sm.a_full[s], 256); }
+    for (int s = 0; s < kBwdStages; ++s) { mbar_init(&sm.t_full[s], 1); mbar_init(&sm.t_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
@@ -574,8 +640,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
         tma_bulk_g2s(sm.own + 2 * kOperandBytes, own_src + 4 * kOperandBytes, 2 * kOperandBytes, &sm.c_full);   // dOh | dOl
       }
       for (int i = 0; i < nT; ++i) {
-        const int st = i % kStages;
-        mbar_wait(&sm.t_empty[st], ((i / kStages) & 1) ^ 1);
+        const int st = i % kBwdStages;
+        mbar_wait(&sm.t_empty[st], ((i / kBwdStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&sm.t_full[st], kOthBytes);
         tma_bulk_g2s(sm.oth[st], oth_src + (size_t)i * kOthBytes, kOthBytes, &sm.t_full[st]);
       }
@@ -591,40 +657,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
       constexpr uint32_t oS = 0, oP = DKDV ? 4 * kOperandBytes : 2 * kOperandBytes;
       constexpr uint32_t oB0 = DKDV ? 6 * kOperandBytes : 4 * kOperandBytes;                       // dO^T (dV) / K^T (dQ)
       constexpr uint32_t oB1 = 2 * kOperandBytes;                                                  // Q'^T (dK)
-      auto accumulate = [&](int v) {
-        const int b = v & 1;
-        const uint32_t ob = smem_u32(sm.oth[(v >> 1) % kStages]) + (uint32_t)(v & 1) * 1024u;      // 64 k = 8 core matrices of 128 B
-        const uint32_t pa = smem_u32(sm.pa[b][0]);
-        mbar_wait(&sm.a_full[b], (v >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < kSub / 16; ++kk) {
-          const uint32_t ko = kk * 256;
-          const uint32_t acc = (v > 0 || kk > 0) ? 1u : 0u;
-          if (DKDV) {
-            umma_bf16(tmem + kTmAcc0, make_desc(pa + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
-            umma_bf16(tmem + kTmAcc0, make_desc(pa + ko, 128, kSboSub), make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16(tmem + kTmAcc0, make_desc(pa + kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16(tmem + kTmAcc1, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, acc);
-            umma_bf16(tmem + kTmAcc1, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB1 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16(tmem + kTmAcc1, make_desc(pa + 3 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, 1);
-          } else {
-            umma_bf16(tmem + kTmAcc0, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
-            umma_bf16(tmem + kTmAcc0, make_desc(pa + 2 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16(tmem + kTmAcc0, make_desc(pa + 3 * kSubBytes + ko, 128, kSboSub), make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
-          }
-        }
-        umma_commit(&sm.pa_free[b]);
-        if (v & 1) umma_commit(&sm.t_empty[(v >> 1) % kStages]);
-      };
-      mbar_wait(&sm.c_full, 0);
-      for (int u = 0; u < U; ++u) {
-        const int b = u & 1, n = u >> 1, st = n % kStages;
-        if (b == 0) mbar_wait(&sm.t_full[st], (n / kStages) & 1);
-        if (n >= 1) mbar_wait(&sm.s_free[b], (n - 1) & 1);
-        tc_fence_after();
+      auto scores = [&](int u) {                          // S(u), dP(u) -> TMEM stage u & 1
+        const int b = u & 1, n = u >> 1, st = n % kBwdStages;
+        if (b == 0) { mbar_wait(&sm.t_full[st], (n / kBwdStages) & 1); tc_fence_after(); }
         const uint32_t ob = smem_u32(sm.oth[st]) + (uint32_t)b * 2048u;                            // 64 rows = 8 row groups of 256 B
-        const uint32_t tS = tmem + kTmS + b * kSub, tP = tmem + kTmDP + b * kSub;
+        const uint32_t tS = tmem + b * kTmStage, tP = tS + kSub;
         umma_bf16(tS, make_desc(a0_hi, 128, kSboQK), make_desc(ob + oS, 128, kSboQK), idesc_s, 0);
         umma_bf16(tS, make_desc(a0_hi, 128, kSboQK), make_desc(ob + oS + kOperandBytes, 128, kSboQK), idesc_s, 1);
         umma_bf16(tS, make_desc(a0_lo, 128, kSboQK), make_desc(ob + oS, 128, kSboQK), idesc_s, 1);
@@ -632,9 +669,40 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
         umma_bf16(tP, make_desc(a1_hi, 128, kSboQK), make_desc(ob + oP + kOperandBytes, 128, kSboQK), idesc_s, 1);
         umma_bf16(tP, make_desc(a1_lo, 128, kSboQK), make_desc(ob + oP, 128, kSboQK), idesc_s, 1);
         umma_commit(&sm.s_full[b]);
-        if (u >= 1) accumulate(u - 1);
+      };
+      mbar_wait(&sm.c_full, 0);
+      tc_fence_after();
+      scores(0);
+      scores(1);
+      for (int u = 0; u < U; ++u) {
+        const int b = u & 1, n = u >> 1, st = n % kBwdStages;
+        const uint32_t ob = smem_u32(sm.oth[st]) + (uint32_t)b * 1024u;                            // 64 k = 8 core matrices of 128 B
+        const uint32_t tA = tmem + b * kTmStage;
+        mbar_wait(&sm.a_full[b], n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kSub / 16; ++kk) {
+          // packed operand columns of k-step kk inside the stage: math warp `half` = kk / 2 owns columns [half*32, +32) of
+          // the S part (P hi | P lo, 16 columns each) and of the dP part (dA hi | dA lo)
+          const uint32_t ca = (kk >> 1) * 32 + (kk & 1) * 8;
+          const uint32_t ko = kk * 256;
+          const uint32_t acc = (u > 0 || kk > 0) ? 1u : 0u;
+          if (DKDV) {
+            umma_bf16_ts(tmem + kTmAcc0, tA + ca, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
+            umma_bf16_ts(tmem + kTmAcc0, tA + ca, make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16_ts(tmem + kTmAcc0, tA + ca + 16, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16_ts(tmem + kTmAcc1, tA + kSub + ca, make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, acc);
+            umma_bf16_ts(tmem + kTmAcc1, tA + kSub + ca, make_desc(ob + oB1 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16_ts(tmem + kTmAcc1, tA + kSub + ca + 16, make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, 1);
+          } else {
+            umma_bf16_ts(tmem + kTmAcc0, tA + kSub + ca, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
+            umma_bf16_ts(tmem + kTmAcc0, tA + kSub + ca, make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16_ts(tmem + kTmAcc0, tA + kSub + ca + 16, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
+          }
+        }
+        if (b == 1) umma_commit(&sm.t_empty[st]);         // both sub-tiles of this streamed tile are consumed
+        if (u + 2 < U) scores(u + 2);                     // in issue order behind the MMAs that read this stage
       }
-      accumulate(U - 1);
       umma_commit(&sm.o_full);
     }
   } else {
@@ -643,105 +711,55 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
     const int r = quarter * 32 + lane;                  // row inside the own tile
     const int own_row = own_t * 128 + r;
     const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-    // per-row constants
     float l2_row = 0.f, dl_row = 0.f;
-    bool row_masked = false;
-    const unsigned char* fm = nullptr;
-    bool slow_rows = false;
+    BwdMaskCtx mc;
+    mc.bits = 0u; mc.row_masked = false; mc.fm = nullptr; mc.q0 = 0; mc.Lq = prm.Lq; mc.Lk = prm.Lk; mc.own_row = own_row;
+    bool masked = false;
     if (DKDV) {
-      row_masked = own_row >= prm.Lk;
-      if (!row_masked && prm.mask.key_mask) row_masked = prm.mask.key_mask[(size_t)(bh % prm.mask.n_mask_rows) * prm.Lk + own_row] != 0;
-      fm = prm.mask.full_mask ? prm.mask.full_mask + (size_t)(bh % prm.mask.n_mask_rows) * prm.Lq * prm.Lk : nullptr;
+      mc.row_masked = own_row >= prm.Lk;
+      if (!mc.row_masked && prm.mask.key_mask) mc.row_masked = prm.mask.key_mask[(size_t)(bh % prm.mask.n_mask_rows) * prm.Lk + own_row] != 0;
+      mc.fm = prm.mask.full_mask ? prm.mask.full_mask + (size_t)(bh % prm.mask.n_mask_rows) * prm.Lq * prm.Lk : nullptr;
       // padded rows (own_row >= Lk) may stay on the fast path: their outputs are never stored
-      slow_rows = __any_sync(0xffffffffu, row_masked && own_row < prm.Lk) || fm != nullptr;
+      masked = __any_sync(0xffffffffu, mc.row_masked && own_row < prm.Lk) || mc.fm != nullptr;
     } else {
       const float* stats = reinterpret_cast<const float*>(own_src + 8 * kOperandBytes);
       l2_row = __ldg(stats + r);
       dl_row = __ldg(stats + kTileQ + r);
     }
     uint32_t bits[4] = {0u, 0u, 0u, 0u};
-    bool masked = DKDV ? slow_rows : false;
     for (int u = 0; u < U; ++u) {
-      const int b = u & 1, n = u >> 1, st = n % kStages;
+      const int b = u & 1, n = u >> 1, st = n % kBwdStages;
       const int col0 = b * kSub + half * 32;             // first column (inside the streamed 128-tile) of this thread's 32
       if (!DKDV && b == 0) {
         masked = tile_needs_mask(prm.mask, bh, prm.Lk, n * kTileK, lane);
         if (masked) key_bits(prm.mask, bh, own_row, prm.Lq, prm.Lk, n * kTileK, bits);
       }
-      if (DKDV && b == 0) mbar_wait(&sm.t_full[st], (n / kStages) & 1);     // lse2 / delta of this query tile are in smem
+      if (DKDV && b == 0) mbar_wait(&sm.t_full[st], (n / kBwdStages) & 1);   // lse2 / delta of this query tile are in smem
       mbar_wait(&sm.s_full[b], n & 1);
       tc_fence_after();
+      const uint32_t t_s = t_row + b * kTmStage + half * 32, t_p = t_s + kSub;
       uint32_t sr[32], dr[32];
-      tmem_ld32_issue(t_row + kTmS + b * kSub + half * 32, sr);
-      tmem_ld32_issue(t_row + kTmDP + b * kSub + half * 32, dr);
+      tmem_ld32_issue(t_s, sr);
+      tmem_ld32_issue(t_p, dr);
       tmem_ld32_wait(sr);
       tmem_ld32_wait(dr);
-      tc_fence_before();
-      mbar_arrive(&sm.s_free[b]);                         // the TMEM stage may be overwritten by sub-tile u + 2
-      if (n >= 1) mbar_wait(&sm.pa_free[b], (n - 1) & 1);  // the MMAs of sub-tile u - 2 have consumed this shared stage
-      unsigned char* p_hi = sm.pa[b][0];
-      unsigned char* p_lo = sm.pa[b][1];
-      unsigned char* a_hi = sm.pa[b][2];
-      unsigned char* a_lo = sm.pa[b][3];
       const float* stats = reinterpret_cast<const float*>(sm.oth[st] + 8 * kOperandBytes);
+      uint32_t ph[16], pl[16], ah[16], al[16];
       if (!masked) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p8[8], a8[8];
-          if (DKDV) {
-            const float4 l2a = *reinterpret_cast<const float4*>(stats + col0 + g * 8);
-            const float4 l2b = *reinterpret_cast<const float4*>(stats + col0 + g * 8 + 4);
-            const float4 dla = *reinterpret_cast<const float4*>(stats + kTileQ + col0 + g * 8);
-            const float4 dlb = *reinterpret_cast<const float4*>(stats + kTileQ + col0 + g * 8 + 4);
-            const float l2v[8] = {l2a.x, l2a.y, l2a.z, l2a.w, l2b.x, l2b.y, l2b.z, l2b.w};
-            const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float p = ex2_approx(__uint_as_float(sr[g * 8 + e]) - l2v[e]);
-              p8[e] = p;
-              a8[e] = p * (__uint_as_float(dr[g * 8 + e]) - dlv[e]);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float p = ex2_approx(__uint_as_float(sr[g * 8 + e]) - l2_row);
-              a8[e] = p * (__uint_as_float(dr[g * 8 + e]) - dl_row);
-            }
-          }
-          const int off = kmajor_off(r, half * 32 + g * 8, kSboSub);
-          if (DKDV) store_group(p_hi, p_lo, off, p8);
-          store_group(a_hi, a_lo, off, a8);
-        }
+        bwd_math<DKDV, false>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, ph, pl, ah, al);
       } else {
-        const uint32_t mbits = b ? (half ? bits[3] : bits[2]) : (half ? bits[1] : bits[0]);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p8[8], a8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int i = g * 8 + e;
-            float l2 = l2_row, dl = dl_row;
-            bool mk;
-            if (DKDV) {
-              const int qi = n * kTileQ + col0 + i;
-              l2 = stats[col0 + i];
-              dl = stats[kTileQ + col0 + i];
-              mk = row_masked || qi >= prm.Lq;
-              if (fm && !mk) mk = fm[(size_t)qi * prm.Lk + own_row] != 0;
-            } else {
-              mk = (mbits >> i) & 1u;
-            }
-            float p = ex2_approx(__uint_as_float(sr[i]) - l2);
-            if (mk) p = 0.f;
-            p8[e] = p;
-            a8[e] = p * (__uint_as_float(dr[i]) - dl);
-          }
-          const int off = kmajor_off(r, half * 32 + g * 8, kSboSub);
-          if (DKDV) store_group(p_hi, p_lo, off, p8);
-          store_group(a_hi, a_lo, off, a8);
-        }
+        mc.bits = b ? (half ? bits[3] : bits[2]) : (half ? bits[1] : bits[0]);
+        mc.q0 = n * kTileQ + col0;
+        bwd_math<DKDV, true>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, ph, pl, ah, al);
       }
-      fence_proxy_async();
+      if (DKDV) {
+        tmem_st16_issue(t_s, ph);
+        tmem_st16_issue(t_s + 16, pl);
+      }
+      tmem_st16_issue(t_p, ah);
+      tmem_st16_issue(t_p + 16, al);
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&sm.a_full[b]);
     }
     mbar_wait(&sm.o_full, 0);
@@ -770,6 +788,36 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kBwdTmemCols);
+}
+
+// ---------------------------------------------------------------------------- TMEM read-rate probe (diagnostics)
+template <int X>
+__global__ void __launch_bounds__(512, 1) tmem_ld_probe_kernel(int iters, uint32_t* sink) {
+  __shared__ uint32_t s_base;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&s_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t_row = s_base + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    const uint32_t col = (uint32_t)((it * X + (warp >> 2) * X) & 255);
+    if (X == 32) {
+      uint32_t r[32];
+      tmem_ld32_issue(t_row + col, r);
+      tmem_ld32_wait(r);
+      acc ^= r[0] ^ r[31];
+    } else {
+      float v[16];
+      tmem_ld16(t_row + col, v);
+      acc ^= __float_as_uint(v[0]) ^ __float_as_uint(v[15]);
+    }
+  }
+  if (acc == 0x12345u) *sink = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s_base, 512);
 }
 
 int check_attn(int BH, int Lq, int Lk, int d, int dv) {
@@ -883,6 +931,37 @@ int isa_attention_bwd(const float* q, const float* k, const float* v, const floa
   attn_bwd_kernel<false><<<dim3(nQt, BH), kBwdThreads, smem, stream>>>(bp);   // dQ
   attn_bwd_kernel<true><<<dim3(nKt, BH), kBwdThreads, smem, stream>>>(bp);    // dK, dV
   ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+// Diagnostics: bytes per clock per SM sustained by `warps` (4, 8 or 16) resident warps each issuing back-to-back
+// tcgen05.ld.32x32b.x{cols} (cols = 16 or 32) + wait::ld -- the TMEM read rate the softmax / backward math warps
+// are sized against.  Synchronises the device; scratch = 4 bytes of device memory.
+int isa_selftest_tmem_ld_rate(int warps, int cols, float sm_clock_mhz, void* scratch, float* h_bytes_per_clk_per_sm) {
+  ISA_CHECK_ARG((warps == 4 || warps == 8 || warps == 16) && (cols == 16 || cols == 32) && sm_clock_mhz > 0 && scratch && h_bytes_per_clk_per_sm,
+                "selftest_tmem_ld_rate: bad argument");
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  const int iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  ISA_CUDA(cudaEventCreate(&e0));
+  ISA_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    ISA_CUDA(cudaEventRecord(e0, 0));
+    if (cols == 32) tmem_ld_probe_kernel<32><<<di.num_sms, warps * 32>>>(iters, reinterpret_cast<uint32_t*>(scratch));
+    else tmem_ld_probe_kernel<16><<<di.num_sms, warps * 32>>>(iters, reinterpret_cast<uint32_t*>(scratch));
+    ISA_CUDA(cudaEventRecord(e1, 0));
+    ISA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    ISA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double bytes_per_sm = (double)iters * warps * 32.0 * cols * 4.0;
+  *h_bytes_per_clk_per_sm = (float)(bytes_per_sm / ((double)best * 1e-3 * sm_clock_mhz * 1e6));
   return ISA_OK;
 }
 

@@ -25,4 +25,10 @@ for packed in (0, 1):
         rc = lib.isa_selftest_fma_rate(packed, w, 1965.0, scratch.data_ptr(), ctypes.byref(r))
         _lib.check(rc, "isa_selftest_fma_rate")
         out["fma/clk/SM %s warps=%d (at 1965 MHz)" % ("FFMA2" if packed else "FFMA", w)] = round(r.value, 1)
+for cols in (16, 32):
+    for w in (4, 8, 16):
+        r = ctypes.c_float(0)
+        rc = lib.isa_selftest_tmem_ld_rate(w, cols, 1965.0, scratch.data_ptr(), ctypes.byref(r))
+        _lib.check(rc, "isa_selftest_tmem_ld_rate")
+        out["tmem ld B/clk/SM x%d warps=%d (at 1965 MHz)" % (cols, w)] = round(r.value, 1)
 print(json.dumps(out, indent=1))
