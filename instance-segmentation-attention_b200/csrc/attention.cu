@@ -42,7 +42,7 @@ constexpr int kQTileBytes = 2 * kOperandBytes;      // Qh | Ql
 constexpr int kPBytes = kTileQ * kTileK * 2;        // 32768: one bf16 [128][128] operand
 constexpr int kFwdThreads = 192;
 constexpr int kTmemCols = 256;                      // S: [0,128), O: [128,144)
-constexpr int kBwdThreads = 320;                    // warp 0 producer, warp 1 MMA, warps 2..9 math
+constexpr int kBwdThreads = 384;                    // warp 0 producer, warps 1-2 MMA issuers (even / odd sub-tiles), warp 3 idle, warps 4..11 math
 constexpr int kBwdTmemCols = 512;
 constexpr int kTmemO = 128;
 
@@ -507,7 +507,7 @@ struct BwdParams {
 constexpr int kSub = 64;
 constexpr int kBwdStages = 3;
 constexpr int kTmStage = 128;                           // TMEM columns per stage: S | dP
-constexpr int kTmAcc0 = 256, kTmAcc1 = 272;
+constexpr int kTmAcc = 256;                             // accumulators: [which (dV|dQ, dK)][chain 0/1][32 columns = x B_hi | x B_lo]
 
 struct BwdSmem {
   unsigned char own[4 * kOperandBytes];                 // dQ: Q'h | Q'l | dOh | dOl      dK/dV: Kh | Kl | Vh | Vl
@@ -552,6 +552,40 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+
+// ---- warp-uniform issue: the whole warp runs the issuing code (so descriptors stay in uniform registers and the
+// compiler emits no per-instruction "waterfall" loop) and one elected lane executes the instruction
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_e(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_e(uint32_t elected, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t elected, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(elected)
       : "memory");
 }
 
@@ -608,7 +642,7 @@ template <bool DKDV>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int own_t = blockIdx.x, bh = blockIdx.y;
   const int nT = DKDV ? prm.nQt : prm.nKt;            // streamed tiles
   const int U = 2 * nT;                               // sub-tiles
@@ -618,9 +652,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
   const unsigned char* oth_src = DKDV ? prm.qtiles + (size_t)bh * prm.nQt * kBwdQTileBytes : prm.ktiles + (size_t)bh * prm.nKt * kBwdKTileBytes;
 
   if (threadIdx.x == 0) {
-    mbar_init(&sm.c_full, 1); mbar_init(&sm.o_full, 1);
+    mbar_init(&sm.c_full, 1); mbar_init(&sm.o_full, 2);
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.s_full[s], 1); mbar_init(&sm.a_full[s], 256); }
-    for (int s = 0; s < kBwdStages; ++s) { mbar_init(&sm.t_full[s], 1); mbar_init(&sm.t_empty[s], 1); }
+    for (int s = 0; s < kBwdStages; ++s) { mbar_init(&sm.t_full[s], 1); mbar_init(&sm.t_empty[s], 2); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
@@ -646,68 +680,75 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
         tma_bulk_g2s(sm.oth[st], oth_src + (size_t)i * kOthBytes, kOthBytes, &sm.t_full[st]);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp <= 2) {
+    // ===================== MMA issuers: chain c = warp - 1 owns the sub-tiles u with u % 2 == c, TMEM stage c and its own
+    // accumulators (summed in the epilogue), so the two chains never wait for each other and the per-MMA issue cost
+    // (descriptor arithmetic + R2UR moves of a single thread) is split between two warps
+    {
+      const int c = warp - 1;
+      const uint32_t el = elect_one();
       constexpr uint32_t idesc_s = make_idesc(128, kSub);
-      constexpr uint32_t idesc_o = make_idesc(128, kDP);
-      const uint32_t a0_hi = smem_u32(sm.own), a0_lo = a0_hi + kOperandBytes;                      // A of S:  Q' (dQ) / K (dK,dV)
-      const uint32_t a1_hi = a0_hi + 2 * kOperandBytes, a1_lo = a0_hi + 3 * kOperandBytes;         // A of dP: dO (dQ) / V (dK,dV)
-      // byte offsets inside a streamed tile: B of S, B of dP (row operands), B of the accumulations (transposed operands)
-      constexpr uint32_t oS = 0, oP = DKDV ? 4 * kOperandBytes : 2 * kOperandBytes;
-      constexpr uint32_t oB0 = DKDV ? 6 * kOperandBytes : 4 * kOperandBytes;                       // dO^T (dV) / K^T (dQ)
-      constexpr uint32_t oB1 = 2 * kOperandBytes;                                                  // Q'^T (dK)
-      auto scores = [&](int u) {                          // S(u), dP(u) -> TMEM stage u & 1
-        const int b = u & 1, n = u >> 1, st = n % kBwdStages;
-        if (b == 0) { mbar_wait(&sm.t_full[st], (n / kBwdStages) & 1); tc_fence_after(); }
-        const uint32_t ob = smem_u32(sm.oth[st]) + (uint32_t)b * 2048u;                            // 64 rows = 8 row groups of 256 B
-        const uint32_t tS = tmem + b * kTmStage, tP = tS + kSub;
-        umma_bf16(tS, make_desc(a0_hi, 128, kSboQK), make_desc(ob + oS, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tS, make_desc(a0_hi, 128, kSboQK), make_desc(ob + oS + kOperandBytes, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tS, make_desc(a0_lo, 128, kSboQK), make_desc(ob + oS, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tP, make_desc(a1_hi, 128, kSboQK), make_desc(ob + oP, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tP, make_desc(a1_hi, 128, kSboQK), make_desc(ob + oP + kOperandBytes, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tP, make_desc(a1_lo, 128, kSboQK), make_desc(ob + oP, 128, kSboQK), idesc_s, 1);
-        umma_commit(&sm.s_full[b]);
+      constexpr uint32_t idesc_o2 = make_idesc(128, 2 * kDP);    // A x [B_hi ; B_lo] -> 32 columns
+      constexpr uint32_t idesc_o1 = make_idesc(128, kDP);
+      // descriptors differ from their base only in the 16-byte address field: desc(addr + x) = desc(addr) + (x >> 4)
+      const uint64_t dA0h = make_desc(smem_u32(sm.own), 128, kSboQK);                               // A of S:  Q' (dQ) / K (dK,dV)
+      const uint64_t dA0l = dA0h + (kOperandBytes >> 4);
+      const uint64_t dA1h = dA0h + (2 * kOperandBytes >> 4), dA1l = dA0h + (3 * kOperandBytes >> 4);   // A of dP: dO (dQ) / V (dK,dV)
+      const uint64_t dRow0 = make_desc(smem_u32(sm.oth[0]), 128, kSboQK);                           // row operands of a streamed tile (B of S / dP)
+      const uint64_t dCol0 = make_desc(smem_u32(sm.oth[0]), 128, kSboP);                            // transposed operands (B of the accumulations)
+      constexpr uint32_t oP = (DKDV ? 4 * kOperandBytes : 2 * kOperandBytes) >> 4;
+      constexpr uint32_t oB0 = (DKDV ? 6 * kOperandBytes : 4 * kOperandBytes) >> 4;                 // dO^T (dV) / K^T (dQ)
+      constexpr uint32_t oB1 = (2 * kOperandBytes) >> 4;                                            // Q'^T (dK)
+      constexpr uint32_t oLo = kOperandBytes >> 4;
+      constexpr uint32_t kStageStride = kBwdQTileBytes >> 4;
+      const uint32_t tS = tmem + c * kTmStage, tP = tS + kSub;
+      const uint32_t acc0 = tmem + kTmAcc + c * 32, acc1 = tmem + kTmAcc + 64 + c * 32;
+      auto scores = [&](int n) {                          // S, dP of sub-tile c of streamed tile n -> TMEM stage c
+        const int st = n % kBwdStages;
+        mbar_wait(&sm.t_full[st], (n / kBwdStages) & 1);
+        tc_fence_after();
+        const uint64_t ob = dRow0 + (uint32_t)st * kStageStride + (uint32_t)c * (2048u >> 4);       // 64 rows = 8 row groups of 256 B
+        umma_bf16_e(el, tS, dA0h, ob, idesc_s, 0);
+        umma_bf16_e(el, tS, dA0h, ob + oLo, idesc_s, 1);
+        umma_bf16_e(el, tS, dA0l, ob, idesc_s, 1);
+        umma_bf16_e(el, tP, dA1h, ob + oP, idesc_s, 0);
+        umma_bf16_e(el, tP, dA1h, ob + oP + oLo, idesc_s, 1);
+        umma_bf16_e(el, tP, dA1l, ob + oP, idesc_s, 1);
+        umma_commit_e(el, &sm.s_full[c]);
       };
       mbar_wait(&sm.c_full, 0);
       tc_fence_after();
       scores(0);
-      scores(1);
-      for (int u = 0; u < U; ++u) {
-        const int b = u & 1, n = u >> 1, st = n % kBwdStages;
-        const uint32_t ob = smem_u32(sm.oth[st]) + (uint32_t)b * 1024u;                            // 64 k = 8 core matrices of 128 B
-        const uint32_t tA = tmem + b * kTmStage;
-        mbar_wait(&sm.a_full[b], n & 1);
+      for (int n = 0; n < nT; ++n) {
+        const int st = n % kBwdStages;
+        const uint64_t ob = dCol0 + (uint32_t)st * kStageStride + (uint32_t)c * (1024u >> 4);       // 64 k = 8 core matrices of 128 B
+        mbar_wait(&sm.a_full[c], n & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kSub / 16; ++kk) {
           // packed operand columns of k-step kk inside the stage: math warp `half` = kk / 2 owns columns [half*32, +32) of
           // the S part (P hi | P lo, 16 columns each) and of the dP part (dA hi | dA lo)
           const uint32_t ca = (kk >> 1) * 32 + (kk & 1) * 8;
-          const uint32_t ko = kk * 256;
-          const uint32_t acc = (u > 0 || kk > 0) ? 1u : 0u;
+          const uint32_t ko = (kk * 256) >> 4;
+          const uint32_t acc = (n > 0 || kk > 0) ? 1u : 0u;
           if (DKDV) {
-            umma_bf16_ts(tmem + kTmAcc0, tA + ca, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
-            umma_bf16_ts(tmem + kTmAcc0, tA + ca, make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16_ts(tmem + kTmAcc0, tA + ca + 16, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16_ts(tmem + kTmAcc1, tA + kSub + ca, make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, acc);
-            umma_bf16_ts(tmem + kTmAcc1, tA + kSub + ca, make_desc(ob + oB1 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16_ts(tmem + kTmAcc1, tA + kSub + ca + 16, make_desc(ob + oB1 + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16_ts_e(el, acc0, tS + ca, ob + oB0 + ko, idesc_o2, acc);          // P_hi x [dO_hi ; dO_lo]
+            umma_bf16_ts_e(el, acc0, tS + ca + 16, ob + oB0 + ko, idesc_o1, 1);       // P_lo x dO_hi
+            umma_bf16_ts_e(el, acc1, tP + ca, ob + oB1 + ko, idesc_o2, acc);          // dA_hi x [Q'_hi ; Q'_lo]
+            umma_bf16_ts_e(el, acc1, tP + ca + 16, ob + oB1 + ko, idesc_o1, 1);       // dA_lo x Q'_hi
           } else {
-            umma_bf16_ts(tmem + kTmAcc0, tA + kSub + ca, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, acc);
-            umma_bf16_ts(tmem + kTmAcc0, tA + kSub + ca, make_desc(ob + oB0 + kOperandBytes + ko, 128, kSboP), idesc_o, 1);
-            umma_bf16_ts(tmem + kTmAcc0, tA + kSub + ca + 16, make_desc(ob + oB0 + ko, 128, kSboP), idesc_o, 1);
+            umma_bf16_ts_e(el, acc0, tP + ca, ob + oB0 + ko, idesc_o2, acc);          // dA_hi x [K_hi ; K_lo]
+            umma_bf16_ts_e(el, acc0, tP + ca + 16, ob + oB0 + ko, idesc_o1, 1);       // dA_lo x K_hi
           }
         }
-        if (b == 1) umma_commit(&sm.t_empty[st]);         // both sub-tiles of this streamed tile are consumed
-        if (u + 2 < U) scores(u + 2);                     // in issue order behind the MMAs that read this stage
+        umma_commit_e(el, &sm.t_empty[st]);                     // this chain is done with the streamed tile (the barrier counts both chains)
+        if (n + 1 < nT) scores(n + 1);                    // in issue order behind the MMAs that read this TMEM stage
       }
-      umma_commit(&sm.o_full);
+      umma_commit_e(el, &sm.o_full);
     }
-  } else {
-    // ===================== 8 math warps: TMEM quarter = warp % 4, 32-column half = (warp - 2) / 4 =====================
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+  } else if (warp >= 4) {
+    // ===================== 8 math warps: TMEM quarter = warp % 4, 32-column half = (warp - 4) / 4 =====================
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
     const int r = quarter * 32 + lane;                  // row inside the own tile
     const int own_row = own_t * 128 + r;
     const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -764,10 +805,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
     }
     mbar_wait(&sm.o_full, 0);
     tc_fence_after();
-    if (DKDV) {
-      float o[16];
-      tmem_ld16(t_row + (half == 0 ? kTmAcc0 : kTmAcc1), o);
-      if (own_row < prm.Lk) {
+    if (DKDV || half == 0) {
+      // result = sum over the two chains and the [x B_hi | x B_lo] column halves of this accumulator
+      float o[16], t[16];
+      const uint32_t ta = t_row + kTmAcc + (DKDV && half == 1 ? 64 : 0);
+      tmem_ld16(ta, o);
+#pragma unroll
+      for (int part = 1; part < 4; ++part) {
+        tmem_ld16(ta + part * 16, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] += t[i];
+      }
+      if (!DKDV) {
+        if (own_row < prm.Lq) {
+          float* dst = prm.dq + ((size_t)bh * prm.Lq + own_row) * prm.d;
+          for (int i = 0; i < prm.d; ++i) dst[i] = o[i] * prm.inv_t;
+        }
+      } else if (own_row < prm.Lk) {
         if (half == 0) {
           float* dst = prm.dv + ((size_t)bh * prm.Lk + own_row) * prm.dv_dim;
           for (int c = 0; c < prm.dv_dim; ++c) dst[c] = o[c];
@@ -775,13 +829,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
           float* dst = prm.dk + ((size_t)bh * prm.Lk + own_row) * prm.d;
           for (int c = 0; c < prm.d; ++c) dst[c] = o[c] * 0.6931471805599453f;   // ln 2: S was in the exp2 domain
         }
-      }
-    } else if (half == 0) {
-      float o[16];
-      tmem_ld16(t_row + kTmAcc0, o);
-      if (own_row < prm.Lq) {
-        float* dst = prm.dq + ((size_t)bh * prm.Lq + own_row) * prm.d;
-        for (int i = 0; i < prm.d; ++i) dst[i] = o[i] * prm.inv_t;
       }
     }
   }
