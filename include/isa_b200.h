@@ -34,14 +34,14 @@ typedef void* isa_stream_t; /* cudaStream_t */
 const char* isa_last_error(void);
 int isa_version(void);
 int isa_num_sms(int* out);
-/* Diagnostics: mean device time (us) of one grid-wide barrier between ctas_per_sm * num_sms co-resident CTAs
- * (variant 0: fence per thread + sleeping poll, 1: cooperative-groups style) -- the fixed cost per iteration of the
- * persistent cooperative kernels.  Synchronises the device; scratch = 8 bytes of device memory; result on the host. */
 /* Diagnostics: FP32 multiply-adds per clock per SM sustained by scalar FFMA (packed = 0) or fma.rn.f32x2 / FFMA2
  * (packed = 1) with warps_per_sm resident warps of 16 independent chains each; synchronises the device. */
 int isa_selftest_fma_rate(int packed, int warps_per_sm, float sm_clock_mhz, void* scratch, float* h_fma_per_clk_per_sm);
 /* Diagnostics: TMEM read rate (bytes per clock per SM) of `warps` in {4,8,16} warps issuing tcgen05.ld.32x32b.x{cols}, cols in {16,32}. */
 int isa_selftest_tmem_ld_rate(int warps, int cols, float sm_clock_mhz, void* scratch, float* h_bytes_per_clk_per_sm);
+/* Diagnostics: mean device time (us) of one grid-wide barrier between ctas_per_sm * num_sms co-resident CTAs
+ * (variant 0: fence per thread + sleeping poll, 1: cooperative-groups style) -- the fixed cost per iteration of the
+ * persistent cooperative kernels.  Synchronises the device; scratch = 8 bytes of device memory; result on the host. */
 int isa_selftest_grid_barrier(int ctas_per_sm, int threads, int iters, int variant, void* scratch, float* h_us_per_barrier);
 
 /* ------------------------------------------------------------------ discriminative loss
@@ -253,6 +253,43 @@ int isa_local_attention_fwd(const float* Q, const float* K, const float* V, cons
 int isa_local_attention_bwd(const float* Q, const float* K, const float* V, const float* P, const float* dout, int Bh,
                             int dk, int dv, int h, int w, int dil, float scale, float* dQ, float* dK, float* dV,
                             float* dS_workspace, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ channels-last epilogues, residual + LayerNorm
+ * Token-major [rows][C] f32 matrices (an NHWC activation is one with rows = N*H*W).
+ *   isa_bias_act_*       the `+ bias` / ReLU that follows every convolution of the embedding network
+ *                        (/root/reference/code/lib/archs/modules/vgg16.py:82-140 conv+ReLU stacks, reseg.py:117-121
+ *                        transposed convolutions + ReLU): y = act(x + b) in place on a bias-free convolution output;
+ *                        backward gx = gy * (y > 0) and dbias = column sums of gx in one pass (deterministic).
+ *   isa_add_layernorm_*  MultiHeadAttention's `self.layer_norm(output + residual)`
+ *                        (/root/reference/code/lib/archs/modules/utils.py:218-219), nn.LayerNorm semantics (biased
+ *                        variance, eps inside the root); backward returns the gradient of (x + res) and of gamma/beta. */
+size_t isa_bias_act_workspace_bytes(int C);
+int isa_bias_act_fwd(float* x, const float* bias, long long rows, int C, int relu, isa_stream_t stream);
+int isa_bias_act_bwd(const float* gy, const float* y, float* gx, float* dbias, long long rows, int C, int relu, void* workspace,
+                     size_t workspace_bytes, isa_stream_t stream);
+size_t isa_add_layernorm_workspace_bytes(long long rows, int C);
+int isa_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, long long rows, int C, float eps,
+                          float* y, float* stats, isa_stream_t stream);
+int isa_add_layernorm_bwd(const float* gy, const float* x, const float* res, const float* gamma, const float* stats, long long rows,
+                          int C, float* gv, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ pixel heads (1x1 convolutions -> NCHW planes)
+ * /root/reference/code/lib/archs/reseg.py:122-126: the semantic and the embedding head are 1x1 convolutions over the
+ * same feature map (here the channel concatenation [up-sampled features | skip], never materialised).
+ *   xa [P][Ca], xb [P][Cb] f32 NHWC sources (P = n * HW pixels; xb may be NULL with Cb = 0; Ca, Cb even);
+ *   w [Co0 + Co1][Ca + Cb] the two heads' weights stacked, bias [Co0 + Co1] or NULL;
+ *   out0 [n][Co0][HW], out1 [n][Co1][HW] f32 NCHW planes -- what isa_disc_loss_* / isa_fg_compact read.
+ * Backward writes the NHWC source gradients ga / gb (either may be NULL) from the NCHW output gradients g0 / g1 (either
+ * may be NULL = zero); weight and bias gradients are plain GEMMs / row sums (host side).  Co0 + Co1 <= 32. */
+int isa_pixel_heads_fwd(const float* xa, int Ca, const float* xb, int Cb, const float* w, const float* bias, float* out0, int Co0,
+                        float* out1, int Co1, long long P, int HW, isa_stream_t stream);
+int isa_pixel_heads_bwd(const float* g0, int Co0, const float* g1, int Co1, const float* w, float* ga, int Ca, float* gb, int Cb,
+                        long long P, int HW, isa_stream_t stream);
+/* dw_db = [ dw [Co0+Co1][Ca+Cb] | db [Co0+Co1] ] from the NCHW output gradients and the NHWC sources (deterministic:
+ * per-CTA partials in the workspace, fixed-order final sum). */
+size_t isa_pixel_heads_wgrad_workspace_bytes(int Ca, int Cb, int Co0, int Co1);
+int isa_pixel_heads_wgrad(const float* g0, int Co0, const float* g1, int Co1, const float* xa, int Ca, const float* xb, int Cb,
+                          long long P, int HW, float* dw_db, void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,20 @@ SIGNATURES = {
                                         c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "isa_local_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "isa_bias_act_workspace_bytes": (c_size_t, [c_int]),
+    "isa_bias_act_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "isa_bias_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "isa_add_layernorm_workspace_bytes": (c_size_t, [c_longlong, c_int]),
+    "isa_add_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "isa_add_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_pixel_heads_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                    c_longlong, c_int, c_void_p]),
+    "isa_pixel_heads_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                    c_longlong, c_int, c_void_p]),
+    "isa_pixel_heads_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "isa_pixel_heads_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_longlong, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_split_bf16x3": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_longlong,
                                  c_longlong, c_int, c_longlong, c_int, c_int, c_int, c_void_p]),
 }
@@ -103,10 +117,12 @@ class IsaError(RuntimeError):
 KERNELS_PER_CALL = {
     "isa_disc_loss_fwd": 2, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1,
     "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
-    "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 2,
+    "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 3,
     "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1, "isa_split_bf16x3": 1,
     "isa_masked_softmax_hw_fwd": 2, "isa_masked_softmax_hw_bwd": 3, "isa_row_dot": 2, "isa_row_affine": 1,
     "isa_readout_fwd": 1, "isa_readout_bwd": 1, "isa_local_attention_fwd": 1, "isa_local_attention_bwd": 2,
+    "isa_bias_act_fwd": 1, "isa_bias_act_bwd": 2, "isa_add_layernorm_fwd": 1, "isa_add_layernorm_bwd": 2,
+    "isa_pixel_heads_fwd": 1, "isa_pixel_heads_bwd": 1, "isa_pixel_heads_wgrad": 2,
 }
 
 

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .attention import MultiHeadAttention
+from .pointwise import ConvBiasAct, ConvTransposeBiasAct, pixel_heads, thin_linear
 from .renet import ReNet
 
 
@@ -31,7 +32,9 @@ class SkipVGG16(nn.Module):
         def block(cin, cout, n):
             layers = []
             for i in range(n):
-                layers += [nn.Conv2d(cin if i == 0 else cout, cout, 3, padding=1), nn.ReLU(inplace=True)]
+                # bias + ReLU run as one in-place epilogue kernel (pointwise.py); the Identity keeps the
+                # Sequential indices -- and with them the state_dict keys -- of the conv / ReLU pairs
+                layers += [ConvBiasAct(cin if i == 0 else cout, cout, 3, padding=1, relu=True), nn.Identity()]
             return nn.Sequential(*layers)
 
         self.stage1 = block(n_input, 64, 2)
@@ -64,7 +67,7 @@ class EmbeddingPath(nn.Module):
         x = self.renet2(x)                       # (N, 2n, h, w), channels_last memory
         n, c, h, w = x.shape
         tok = x.permute(0, 2, 3, 1).reshape(n, h * w, c)   # no copy: channels_last
-        a = self.attn_in(tok)
+        a = thin_linear(tok, self.attn_in)
         mask = None
         if fg_mask is not None:                  # (N, h, w) 1 = foreground: attend to foreground keys only
             mask = (fg_mask.reshape(n, 1, h * w) == 0)
@@ -87,13 +90,14 @@ class ReSeg(nn.Module):
         self.base = SkipVGG16(n_input)
         self.path = EmbeddingPath(self.base.n_filters, n_units, n_head, n_embedding, d_k, d_v)
         c = self.path.n_out
-        self.upsampling1 = nn.ConvTranspose2d(c, 100, kernel_size=(2, 2), stride=(2, 2))
-        self.relu1 = nn.ReLU()
-        self.upsampling2 = nn.ConvTranspose2d(100 + 128, 50, kernel_size=(2, 2), stride=(2, 2))
-        self.relu2 = nn.ReLU()
-        self.sem_seg_output = nn.Conv2d(50 + 64, n_classes, kernel_size=(1, 1), stride=(1, 1))
+        # transposed convolutions with their ReLU (reseg.py:117-121) fused into the epilogue kernel
+        self.upsampling1 = ConvTransposeBiasAct(c, 100, kernel_size=(2, 2), stride=(2, 2), relu=True)
+        self.relu1 = nn.Identity()
+        self.upsampling2 = ConvTransposeBiasAct(100 + 128, 50, kernel_size=(2, 2), stride=(2, 2), relu=True)
+        self.relu2 = nn.Identity()
+        self.sem_seg_output = ConvBiasAct(50 + 64, n_classes, kernel_size=(1, 1), stride=(1, 1))
         if use_instance_seg:
-            self.ins_seg_output = nn.Conv2d(50 + 64, n_embedding, kernel_size=(1, 1), stride=(1, 1))
+            self.ins_seg_output = ConvBiasAct(50 + 64, n_embedding, kernel_size=(1, 1), stride=(1, 1))
 
     def forward(self, training, *_input):
         x = _input[0]
@@ -102,8 +106,9 @@ class ReSeg(nn.Module):
         y = self.relu1(self.upsampling1(y))
         y = torch.cat((y, s2), dim=1)
         y = self.relu2(self.upsampling2(y))
-        y = torch.cat((y, s1), dim=1)
-        sem_seg_out = self.sem_seg_output(y)
+        # both 1x1 heads in one pass over (y | s1) -- the concatenation is never materialised -- straight to the NCHW
+        # planes the loss / clustering kernels read
         if self.use_instance_seg:
-            return sem_seg_out, self.ins_seg_output(y).contiguous()
+            return pixel_heads(y, s1, self.sem_seg_output, self.ins_seg_output)
+        sem_seg_out, _ = pixel_heads(y, s1, self.sem_seg_output)
         return sem_seg_out, sem_seg_out.argmax(1, keepdim=True).float()

@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .pointwise import add_layer_norm, thin_linear
 
 
 def _prep_mask(mask, BH, Lq, Lk, device):
@@ -166,9 +167,9 @@ class MultiHeadAttention(nn.Module):
         sz_b, len_k, _ = k.size()
         sz_b, len_v, _ = v.size()
         residual = q
-        q = self.w_qs(q).view(sz_b, len_q, n_head, d_k)
-        k = self.w_ks(k).view(sz_b, len_k, n_head, d_k)
-        v = self.w_vs(v).view(sz_b, len_v, n_head, d_v)
+        q = thin_linear(q, self.w_qs).view(sz_b, len_q, n_head, d_k)
+        k = thin_linear(k, self.w_ks).view(sz_b, len_k, n_head, d_k)
+        v = thin_linear(v, self.w_vs).view(sz_b, len_v, n_head, d_v)
         q = q.permute(2, 0, 1, 3).contiguous().view(-1, len_q, d_k)  # (n*b) x lq x dk
         k = k.permute(2, 0, 1, 3).contiguous().view(-1, len_k, d_k)
         v = v.permute(2, 0, 1, 3).contiguous().view(-1, len_v, d_v)
@@ -178,8 +179,8 @@ class MultiHeadAttention(nn.Module):
             output, attn = self.attention(q, k, v, mask=mask)
             output = output.view(n_head, sz_b, len_q, d_v)
             output = output.permute(1, 2, 0, 3).contiguous().view(sz_b, len_q, -1)  # b x lq x (n*dv)
-            output = self.dropout(self.fc(output))
-            output = self.layer_norm(output + residual)
+            output = self.dropout(thin_linear(output, self.fc))
+            output = add_layer_norm(output, residual, self.layer_norm)
             return output, attn
         correlation = self.attention(q, k, v, mask=None, last=True)
         correlation = torch.sigmoid(correlation)
