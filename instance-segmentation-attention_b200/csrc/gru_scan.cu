@@ -25,6 +25,7 @@
 //   those arrays on the host side.
 #include "isa_common.cuh"
 #include "isa_ptx.cuh"
+#include "isa_tcgen05.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -734,6 +735,219 @@ __global__ void __launch_bounds__(RegBwdCfg<NU, S>::NT, 1) gru_bwd_reg_kernel(co
   }
 }
 
+
+// ================================================================================================ tensor-core scan
+// The recurrent product of a step, G[3n x S] = W_hh[3n x n] h[n x S], on the 5th-generation tensor cores:
+//   * W_hh lives in TENSOR MEMORY for the whole sweep as the A operand (one 128-row tile per gate, rows = hidden
+//     units, bf16 hi and lo parts: 6 x 56 = 336 columns for n = 100), so a step's MMAs read only the 7 KB B operand;
+//   * h_{t-1} of the CTA's <= 16 sequences is the B operand [N = 16][K = n] in shared memory (bf16 hi / lo, canonical
+//     K-major core matrices), rewritten every step by the gate threads;
+//   * every product is a_hi b_hi + a_hi b_lo + a_lo b_hi with fp32 accumulation (error ~2^-16, like the projections):
+//     3 gates x 7 k-steps x 3 = 63 tcgen05.mma (N = 16) per step, ~0.5 k cycles, issued warp-uniformly by one warp;
+//   * the accumulators D_g [128 x 16] come back with tcgen05.ld: TMEM lane = hidden unit, so thread j holds the three
+//     gate pre-activations of unit j for all 16 sequences and does the gate math (ex2 / rcp on the MUFU), keeps h in
+//     registers, stores h / the stash rows (coalesced over j) and writes the next B operand;
+//   * the per-step gx rows arrive through a 3-stage TMA bulk-copy ring filled by a dedicated producer warp.
+// A step is ~1.5 k cycles of latency (MMA 0.5 k + gate math 0.7 k + hand-offs), below the ~2.3 k cycles the step's HBM
+// traffic costs at 148 CTAs, against 8.6 k cycles for the FFMA2 register kernel above.
+template <int NU>
+struct TcCfg {
+  static constexpr int KP = (NU + 15) / 16 * 16;      // reduction length padded to the MMA's K = 16
+  static constexpr int KSTEPS = KP / 16;
+  static constexpr int ACOLS = KP / 2;                // TMEM columns of one (gate, part) A tile: packed bf16 pairs
+  static constexpr int TM_D = 6 * ACOLS;              // accumulators: gate g at TM_D + 16 g
+  static constexpr int NSEQ = 16;                     // MMA N
+  static constexpr int SBO_B = (KP / 8) * 128;        // byte stride between 8-sequence groups of the B operand
+  static constexpr int B_PART = 2 * SBO_B;            // bytes of one part (hi or lo) of B
+  static constexpr int STAGES = 3;
+  static constexpr int NT = 192;                      // warp 0 producer, warp 1 MMA issuer, warps 2..5 gate threads
+  static constexpr size_t gx_bytes = (size_t)STAGES * NSEQ * 3 * NU * sizeof(float);
+  static constexpr size_t used_bytes = gx_bytes + 2 * B_PART + 16 * 8 + NSEQ * 8 + 16 + 128;
+  // the CTA allocates all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs can never
+  // share an SM (the second one would spin in tcgen05.alloc until the first retires)
+  static constexpr size_t smem_bytes = used_bytes > 120 * 1024 ? used_bytes : 120 * 1024;
+  static_assert(TM_D + 3 * 16 <= 512 && NU <= 128 && NU % 4 == 0, "unsupported width");
+};
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, __fdividef(1.f, 1.f + ex2_approx(-2.8853900817779268f * x)), -1.f); }
+
+template <int NU>
+__global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruFwdParams prm, const int S) {
+  using Cfg = TcCfg<NU>;
+  constexpr int N3 = 3 * NU, NSEQ = Cfg::NSEQ, STAGES = Cfg::STAGES;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  float* s_gx = reinterpret_cast<float*>(sm);                               // [STAGES][16][3n]
+  unsigned char* s_b = sm + Cfg::gx_bytes;                                   // B operand: hi part | lo part
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + 2 * Cfg::B_PART);      // gx_full[3] gx_empty[3] h_full d_full
+  long long* s_tok = reinterpret_cast<long long*>(s_bar + 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tok + NSEQ);
+  uint64_t* gx_full = s_bar;
+  uint64_t* gx_empty = s_bar + STAGES;
+  uint64_t* h_full = s_bar + 2 * STAGES;
+  uint64_t* d_full = s_bar + 2 * STAGES + 1;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int d = blockIdx.y;
+  const int q0 = blockIdx.x * S;
+  const int T = prm.T;
+  const int n_valid = min(S, prm.n_seq - q0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&gx_full[i], 1); mbar_init(&gx_empty[i], 128); }
+    mbar_init(h_full, 128);
+    mbar_init(d_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < (int)((Cfg::gx_bytes + 2 * Cfg::B_PART) / 4); i += Cfg::NT) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+  if (threadIdx.x < NSEQ) s_tok[threadIdx.x] = (int)threadIdx.x < n_valid ? tok_base(prm.map, q0 + threadIdx.x) : -1;
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  fence_proxy_async();          // the zero-filled B operand is read through the async proxy by the first MMAs
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int quarter = warp & 3;
+  const int j = quarter * 32 + lane;                       // hidden unit of a gate thread = TMEM lane
+  const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
+  if (warp >= 2) {
+    // W_hh -> TMEM (once): row j of gate g, split into bf16 hi / lo, two values per 32-bit column
+    const float* __restrict__ wsrc = prm.w_hh + (size_t)d * N3 * NU;
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll 1
+      for (int c = 0; c < Cfg::KSTEPS; ++c) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = c * 16 + 2 * e;
+          float a = 0.f, b = 0.f;
+          if (j < NU && k < NU) {          // NU even: k and k + 1 are valid together
+            const float2 v = __ldg(reinterpret_cast<const float2*>(wsrc + (size_t)(g * NU + j) * NU + k));
+            a = v.x; b = v.y;
+          }
+          split2(a, b, hi[e], lo[e]);
+        }
+        tmem_st8_issue(t_row + (g * 2) * Cfg::ACOLS + c * 8, hi);
+        tmem_st8_issue(t_row + (g * 2 + 1) * Cfg::ACOLS + c * 8, lo);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== producer: gx rows of step st -> stage st % STAGES =====================
+    for (int st = 0; st < T; ++st) {
+      const int stage = st % STAGES;
+      mbar_wait(&gx_empty[stage], ((st / STAGES) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&gx_full[stage], (uint32_t)n_valid * N3 * 4u);
+      __syncwarp();
+      if (lane < n_valid) {
+        const int t = (d == 0) ? st : T - 1 - st;
+        const long long tok = s_tok[lane] + (long long)t * prm.map.t_stride;
+        tma_bulk_g2s(s_gx + ((size_t)stage * NSEQ + lane) * N3, prm.gx + ((size_t)tok * 2 + d) * N3, N3 * 4u, &gx_full[stage]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform, one elected lane) =====================
+    const uint32_t el = elect_one();
+    constexpr uint32_t idesc = make_idesc(128, NSEQ);
+    const uint64_t b_hi = make_desc(smem_u32(s_b), 128, Cfg::SBO_B);
+    const uint64_t b_lo = make_desc(smem_u32(s_b + Cfg::B_PART), 128, Cfg::SBO_B);
+    for (int step = 0; step < T; ++step) {
+      if (step > 0) mbar_wait(h_full, (step - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const uint32_t dcol = tmem + Cfg::TM_D + g * 16;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
+          const uint32_t a_hi = tmem + (g * 2) * Cfg::ACOLS + kk * 8, a_lo = tmem + (g * 2 + 1) * Cfg::ACOLS + kk * 8;
+          const uint32_t ko = (kk * 256) >> 4;
+          umma_bf16_ts_e(el, dcol, a_hi, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
+          umma_bf16_ts_e(el, dcol, a_hi, b_lo + ko, idesc, 1u);
+          umma_bf16_ts_e(el, dcol, a_lo, b_hi + ko, idesc, 1u);
+        }
+      }
+      umma_commit_e(el, d_full);
+    }
+  } else {
+    // ===================== gate threads: unit j, all sequences =====================
+    const bool unit = j < NU;
+    const int jj = unit ? j : 0;
+    const float bhr = __ldg(prm.b_hh + d * N3 + jj) + (prm.b_ih ? __ldg(prm.b_ih + d * N3 + jj) : 0.f);
+    const float bhz = __ldg(prm.b_hh + d * N3 + NU + jj) + (prm.b_ih ? __ldg(prm.b_ih + d * N3 + NU + jj) : 0.f);
+    const float bhn = __ldg(prm.b_hh + d * N3 + 2 * NU + jj);
+    const float bin = prm.b_ih ? __ldg(prm.b_ih + d * N3 + 2 * NU + jj) : 0.f;
+    float hreg[NSEQ];
+#pragma unroll
+    for (int s = 0; s < NSEQ; ++s) hreg[s] = 0.f;
+    unsigned char* b_base = s_b + (jj >> 3) * 128 + (jj & 7) * 2;
+    for (int step = 0; step < T; ++step) {
+      const int t = (d == 0) ? step : T - 1 - step;
+      const int stage = step % STAGES;
+      mbar_wait(d_full, step & 1);
+      tc_fence_after();
+      uint32_t ar[16], az[16], an[16];
+      tmem_ld16_issue(t_row + Cfg::TM_D, ar);
+      tmem_ld16_issue(t_row + Cfg::TM_D + 16, az);
+      tmem_ld16_issue(t_row + Cfg::TM_D + 32, an);
+      tmem_ld16_wait(ar);
+      tmem_ld16_wait(az);
+      tmem_ld16_wait(an);
+      mbar_wait(&gx_full[stage], (step / STAGES) & 1);
+      const float* __restrict__ gxs = s_gx + (size_t)stage * NSEQ * N3;
+      if (unit) {
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+          const float xr = gxs[s * N3 + j], xz = gxs[s * N3 + NU + j], xn = gxs[s * N3 + 2 * NU + j];
+          const float hn = __uint_as_float(an[s]) + bhn;
+          const float r = sigmoid_fast(xr + __uint_as_float(ar[s]) + bhr);
+          const float z = sigmoid_fast(xz + __uint_as_float(az[s]) + bhz);
+          const float nn = tanh_fast(xn + bin + r * hn);
+          const float hnew = fmaf(z, hreg[s] - nn, nn);          // (1 - z) n + z h
+          hreg[s] = hnew;
+          const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
+          const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
+          unsigned char* bp = b_base + (s >> 3) * Cfg::SBO_B + (s & 7) * 16;
+          *reinterpret_cast<__nv_bfloat16*>(bp) = hh;
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART) = hl;
+          const long long tb = s_tok[s];
+          if (tb >= 0) {
+            const long long tok = tb + (long long)t * prm.map.t_stride;
+            prm.out[(size_t)tok * (2 * NU) + d * NU + j] = hnew;
+            if (prm.stash) {
+              float* st4 = prm.stash + ((size_t)tok * 2 + d) * (4 * NU) + j;
+              st4[0] = r; st4[NU] = z; st4[2 * NU] = nn; st4[3 * NU] = hn;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();          // B operand writes -> visible to the tensor core's async proxy
+      mbar_arrive(h_full);
+      mbar_arrive(&gx_empty[stage]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int NU>
+int launch_fwd_tc(const GruFwdParams& prm, int S, cudaStream_t stream) {
+  using Cfg = TcCfg<NU>;
+  ISA_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+  dim3 grid((prm.n_seq + S - 1) / S, 2);
+  gru_fwd_tc_kernel<NU><<<grid, Cfg::NT, Cfg::smem_bytes, stream>>>(prm, S);
+  return ISA_OK;
+}
+
 template <int NU, int S>
 int launch_fwd_reg(const GruFwdParams& prm, cudaStream_t stream) {
   using Cfg = RegFwdCfg<NU, S>;
@@ -803,6 +1017,12 @@ int isa_gru_scan_fwd(const float* gx, const float* w_hh, const float* b_hh, cons
   prm.gx = gx; prm.w_hh = w_hh; prm.b_hh = b_hh; prm.b_ih = b_ih; prm.out = out; prm.stash = stash;
   prm.n_seq = n_seq; prm.T = T; prm.n = n_units;
   prm.map.inner = inner; prm.map.outer_stride = outer_tok_stride; prm.map.inner_stride = inner_tok_stride; prm.map.t_stride = t_tok_stride;
+  if (n_units == 100 && aligned16(gx) && !getenv("ISA_GRU_GENERIC") && !getenv("ISA_GRU_REG")) {
+    rc = launch_fwd_tc<100>(prm, pick_S_reg(n_seq, di.num_sms), stream);
+    if (rc) return rc;
+    ISA_CUDA(cudaGetLastError());
+    return ISA_OK;
+  }
   if (n_units == 100 && aligned16(gx) && !getenv("ISA_GRU_GENERIC")) {
     switch (pick_S_reg(n_seq, di.num_sms)) {
       case 16: rc = launch_fwd_reg<100, 16>(prm, stream); break;
