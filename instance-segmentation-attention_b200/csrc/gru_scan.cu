@@ -760,7 +760,8 @@ struct TcCfg {
   static constexpr int SBO_B = (KP / 8) * 128;        // byte stride between 8-sequence groups of the B operand
   static constexpr int B_PART = 2 * SBO_B;            // bytes of one part (hi or lo) of B
   static constexpr int STAGES = 3;
-  static constexpr int NT = 192;                      // warp 0 producer, warp 1 MMA issuer, warps 2..5 gate threads
+  static constexpr int NT = 320;                      // warp 0 producer, warp 1 MMA issuer, warps 2..9 gate threads
+  static constexpr int GATE_THREADS = 256;            // (TMEM quarter = warp % 4) x (sequence half = (warp - 2) / 4)
   static constexpr size_t gx_bytes = (size_t)STAGES * NSEQ * 3 * NU * sizeof(float);
   static constexpr size_t used_bytes = gx_bytes + 2 * B_PART + 16 * 8 + NSEQ * 8 + 16 + 128;
   // the CTA allocates all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs can never
@@ -795,8 +796,8 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
   const int n_valid = min(S, prm.n_seq - q0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&gx_full[i], 1); mbar_init(&gx_empty[i], 128); }
-    mbar_init(h_full, 128);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&gx_full[i], 1); mbar_init(&gx_empty[i], Cfg::GATE_THREADS); }
+    mbar_init(h_full, Cfg::GATE_THREADS);
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
@@ -877,35 +878,52 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
       umma_commit_e(el, d_full);
     }
   } else {
-    // ===================== gate threads: unit j, all sequences =====================
+    // ===================== gate threads: unit j, eight sequences (two warps share a TMEM quarter) =====================
+    constexpr int SH = NSEQ / 2;
+    const int s0 = ((warp - 2) >> 2) * SH;                 // first sequence of this thread
     const bool unit = j < NU;
     const int jj = unit ? j : 0;
     const float bhr = __ldg(prm.b_hh + d * N3 + jj) + (prm.b_ih ? __ldg(prm.b_ih + d * N3 + jj) : 0.f);
     const float bhz = __ldg(prm.b_hh + d * N3 + NU + jj) + (prm.b_ih ? __ldg(prm.b_ih + d * N3 + NU + jj) : 0.f);
     const float bhn = __ldg(prm.b_hh + d * N3 + 2 * NU + jj);
     const float bin = prm.b_ih ? __ldg(prm.b_ih + d * N3 + 2 * NU + jj) : 0.f;
-    float hreg[NSEQ];
+    float hreg[SH];
+    // running output pointers: one 64-bit add per sequence and step instead of the token arithmetic
+    float* po[SH];
+    float* ps[SH];
+    uint32_t valid = 0;
+    const long long t_first = (d == 0) ? 0 : T - 1;
+    const long long dstep = ((d == 0) ? 1 : -1) * prm.map.t_stride;
 #pragma unroll
-    for (int s = 0; s < NSEQ; ++s) hreg[s] = 0.f;
-    unsigned char* b_base = s_b + (jj >> 3) * 128 + (jj & 7) * 2;
+    for (int s = 0; s < SH; ++s) {
+      hreg[s] = 0.f;
+      const long long tb = s_tok[s0 + s];
+      const long long tok = (tb >= 0 ? tb : 0) + t_first * prm.map.t_stride;
+      if (tb >= 0) valid |= 1u << s;
+      po[s] = prm.out + (size_t)tok * (2 * NU) + d * NU + jj;
+      ps[s] = prm.stash ? prm.stash + ((size_t)tok * 2 + d) * (4 * NU) + jj : nullptr;
+    }
+    const long long dout = dstep * (2 * NU), dstash = dstep * (8 * NU);
+    const bool has_stash = prm.stash != nullptr;
+    unsigned char* b_base = s_b + (jj >> 3) * 128 + (jj & 7) * 2 + (s0 >> 3) * Cfg::SBO_B;
+    const uint32_t t_d = t_row + Cfg::TM_D + s0;
     for (int step = 0; step < T; ++step) {
-      const int t = (d == 0) ? step : T - 1 - step;
       const int stage = step % STAGES;
       mbar_wait(d_full, step & 1);
       tc_fence_after();
-      uint32_t ar[16], az[16], an[16];
-      tmem_ld16_issue(t_row + Cfg::TM_D, ar);
-      tmem_ld16_issue(t_row + Cfg::TM_D + 16, az);
-      tmem_ld16_issue(t_row + Cfg::TM_D + 32, an);
-      tmem_ld16_wait(ar);
-      tmem_ld16_wait(az);
-      tmem_ld16_wait(an);
+      uint32_t ar[SH], az[SH], an[SH];
+      tmem_ld8_issue(t_d, ar);
+      tmem_ld8_issue(t_d + 16, az);
+      tmem_ld8_issue(t_d + 32, an);
+      tmem_ld8_wait(ar);
+      tmem_ld8_wait(az);
+      tmem_ld8_wait(an);
       mbar_wait(&gx_full[stage], (step / STAGES) & 1);
-      const float* __restrict__ gxs = s_gx + (size_t)stage * NSEQ * N3;
+      const float* __restrict__ gxs = s_gx + ((size_t)stage * NSEQ + s0) * N3 + jj;
       if (unit) {
 #pragma unroll
-        for (int s = 0; s < NSEQ; ++s) {
-          const float xr = gxs[s * N3 + j], xz = gxs[s * N3 + NU + j], xn = gxs[s * N3 + 2 * NU + j];
+        for (int s = 0; s < SH; ++s) {
+          const float xr = gxs[s * N3], xz = gxs[s * N3 + NU], xn = gxs[s * N3 + 2 * NU];
           const float hn = __uint_as_float(an[s]) + bhn;
           const float r = sigmoid_fast(xr + __uint_as_float(ar[s]) + bhr);
           const float z = sigmoid_fast(xz + __uint_as_float(az[s]) + bhz);
@@ -914,18 +932,18 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
           hreg[s] = hnew;
           const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
           const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
-          unsigned char* bp = b_base + (s >> 3) * Cfg::SBO_B + (s & 7) * 16;
+          unsigned char* bp = b_base + s * 16;                   // SH = 8 sequences = one core-matrix row group
           *reinterpret_cast<__nv_bfloat16*>(bp) = hh;
           *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART) = hl;
-          const long long tb = s_tok[s];
-          if (tb >= 0) {
-            const long long tok = tb + (long long)t * prm.map.t_stride;
-            prm.out[(size_t)tok * (2 * NU) + d * NU + j] = hnew;
-            if (prm.stash) {
-              float* st4 = prm.stash + ((size_t)tok * 2 + d) * (4 * NU) + j;
+          if ((valid >> s) & 1u) {
+            *po[s] = hnew;
+            if (has_stash) {
+              float* st4 = ps[s];
               st4[0] = r; st4[NU] = z; st4[2 * NU] = nn; st4[3 * NU] = hn;
             }
           }
+          po[s] += dout;
+          ps[s] += dstash;
         }
       }
       tc_fence_before();
@@ -945,6 +963,231 @@ int launch_fwd_tc(const GruFwdParams& prm, int S, cudaStream_t stream) {
   ISA_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
   dim3 grid((prm.n_seq + S - 1) / S, 2);
   gru_fwd_tc_kernel<NU><<<grid, Cfg::NT, Cfg::smem_bytes, stream>>>(prm, S);
+  return ISA_OK;
+}
+
+
+// ---- backward (BPTT) on the tensor cores: dh_{t-1}[u] = z dh[u] + sum_g W_hh[g][u] dg[g], with W_hh^T [n x 3n] resident
+// in TMEM as the A operand (2 x 152 columns for n = 100), the step's gate gradients dg = (dr_pre, dz_pre, r dn_pre) of the
+// <= 16 sequences as the B operand [16][3n] in shared memory (bf16 hi / lo), 19 k-steps x 3 = 57 MMAs per step.
+// Gate threads: unit j x eight sequences; their inputs (stash row, h_{t-1}, dL/dh_t) arrive through a TMA ring.
+template <int NU>
+struct TcBwdCfg {
+  static constexpr int K3 = 3 * NU;
+  static constexpr int KP = (K3 + 15) / 16 * 16;
+  static constexpr int KSTEPS = KP / 16;
+  static constexpr int ACOLS = KP / 2;
+  static constexpr int TM_D = 2 * ACOLS;
+  static constexpr int NSEQ = 16;
+  static constexpr int SBO_B = (KP / 8) * 128;
+  static constexpr int B_PART = 2 * SBO_B;
+  static constexpr int STAGES = 3;
+  static constexpr int ROW = 6 * NU;                  // floats per sequence and stage: stash 4n | h_prev n | dout n
+  static constexpr int NT = 320;
+  static constexpr int GATE_THREADS = 256;
+  static constexpr size_t in_bytes = (size_t)STAGES * NSEQ * ROW * sizeof(float);
+  static constexpr size_t used_bytes = in_bytes + 2 * B_PART + 16 * 8 + NSEQ * 8 + 16 + 128;
+  static constexpr size_t smem_bytes = used_bytes > 120 * 1024 ? used_bytes : 120 * 1024;
+  static_assert(TM_D + 16 <= 512 && NU <= 128 && NU % 4 == 0, "unsupported width");
+};
+
+template <int NU>
+__global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const GruBwdParams prm, const int S) {
+  using Cfg = TcBwdCfg<NU>;
+  constexpr int N3 = 3 * NU, NSEQ = Cfg::NSEQ, STAGES = Cfg::STAGES, ROW = Cfg::ROW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  float* s_in = reinterpret_cast<float*>(sm);                                // [STAGES][16][ROW]
+  unsigned char* s_b = sm + Cfg::in_bytes;                                   // B operand: hi part | lo part
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + 2 * Cfg::B_PART);
+  long long* s_tok = reinterpret_cast<long long*>(s_bar + 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tok + NSEQ);
+  uint64_t* in_full = s_bar;
+  uint64_t* in_empty = s_bar + STAGES;
+  uint64_t* g_full = s_bar + 2 * STAGES;
+  uint64_t* d_full = s_bar + 2 * STAGES + 1;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int d = blockIdx.y;
+  const int q0 = blockIdx.x * S;
+  const int T = prm.T;
+  const int n_valid = min(S, prm.n_seq - q0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], Cfg::GATE_THREADS); }
+    mbar_init(g_full, Cfg::GATE_THREADS);
+    mbar_init(d_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < (int)((Cfg::in_bytes + 2 * Cfg::B_PART) / 4); i += Cfg::NT) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+  if (threadIdx.x < NSEQ) s_tok[threadIdx.x] = (int)threadIdx.x < n_valid ? tok_base(prm.map, q0 + threadIdx.x) : -1;
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int quarter = warp & 3;
+  const int j = quarter * 32 + lane;
+  const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
+  if (warp >= 2 && warp < 6) {
+    // W_hh^T -> TMEM (once): row u = j holds W_hh[g][u] over g, bf16 hi / lo pairs (coalesced: lanes run along u)
+    const float* __restrict__ wsrc = prm.w_hh + (size_t)d * N3 * NU;
+#pragma unroll 1
+    for (int c = 0; c < Cfg::KSTEPS; ++c) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int g = c * 16 + 2 * e;
+        const float a = (j < NU && g < N3) ? __ldg(wsrc + (size_t)g * NU + j) : 0.f;
+        const float b = (j < NU && g + 1 < N3) ? __ldg(wsrc + (size_t)(g + 1) * NU + j) : 0.f;
+        split2(a, b, hi[e], lo[e]);
+      }
+      tmem_st8_issue(t_row + c * 8, hi);
+      tmem_st8_issue(t_row + Cfg::ACOLS + c * 8, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== producer: rows of forward step T-1-it -> stage it % STAGES =====================
+    for (int it = 0; it < T; ++it) {
+      const int st = T - 1 - it;
+      const int stage = it % STAGES;
+      mbar_wait(&in_empty[stage], ((it / STAGES) & 1) ^ 1);
+      const uint32_t per_seq = (st > 0 ? 6u : 5u) * NU * 4u;
+      if (lane == 0) mbar_arrive_expect_tx(&in_full[stage], (uint32_t)n_valid * per_seq);
+      __syncwarp();
+      if (lane < n_valid) {
+        const int t = (d == 0) ? st : T - 1 - st;
+        const int tp = (d == 0) ? t - 1 : t + 1;
+        const long long b0 = s_tok[lane];
+        const long long tok = b0 + (long long)t * prm.map.t_stride;
+        float* dst = s_in + ((size_t)stage * NSEQ + lane) * ROW;
+        tma_bulk_g2s(dst, prm.stash + ((size_t)tok * 2 + d) * (4 * NU), 4u * NU * 4u, &in_full[stage]);
+        if (st > 0) {
+          const long long tokp = b0 + (long long)tp * prm.map.t_stride;
+          tma_bulk_g2s(dst + 4 * NU, prm.out + (size_t)tokp * (2 * NU) + d * NU, NU * 4u, &in_full[stage]);
+        }
+        tma_bulk_g2s(dst + 5 * NU, prm.dout + (size_t)tok * (2 * NU) + d * NU, NU * 4u, &in_full[stage]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t el = elect_one();
+    constexpr uint32_t idesc = make_idesc(128, NSEQ);
+    const uint64_t b_hi = make_desc(smem_u32(s_b), 128, Cfg::SBO_B);
+    const uint64_t b_lo = make_desc(smem_u32(s_b + Cfg::B_PART), 128, Cfg::SBO_B);
+    for (int it = 0; it + 1 < T; ++it) {                 // the last step's dh_{-1} is not needed
+      mbar_wait(g_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
+        const uint32_t a_hi = tmem + kk * 8, a_lo = tmem + Cfg::ACOLS + kk * 8;
+        const uint32_t ko = (kk * 256) >> 4;
+        umma_bf16_ts_e(el, tmem + Cfg::TM_D, a_hi, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
+        umma_bf16_ts_e(el, tmem + Cfg::TM_D, a_hi, b_lo + ko, idesc, 1u);
+        umma_bf16_ts_e(el, tmem + Cfg::TM_D, a_lo, b_hi + ko, idesc, 1u);
+      }
+      umma_commit_e(el, d_full);
+    }
+  } else {
+    // ===================== gate threads: unit j, eight sequences =====================
+    constexpr int SH = NSEQ / 2;
+    const int s0 = ((warp - 2) >> 2) * SH;
+    const bool unit = j < NU;
+    const int jj = unit ? j : 0;
+    float dhd[SH];
+    float* pg[SH];
+    float* pn[SH];
+    uint32_t valid = 0;
+    const long long t_first = (d == 0) ? T - 1 : 0;       // time index of forward step T-1
+    const long long dstep = ((d == 0) ? -1 : 1) * prm.map.t_stride;
+#pragma unroll
+    for (int s = 0; s < SH; ++s) {
+      dhd[s] = 0.f;
+      const long long tb = s_tok[s0 + s];
+      const long long tok = (tb >= 0 ? tb : 0) + t_first * prm.map.t_stride;
+      if (tb >= 0) valid |= 1u << s;
+      pg[s] = prm.dgx + ((size_t)tok * 2 + d) * N3 + jj;
+      pn[s] = prm.dghn + ((size_t)tok * 2 + d) * NU + jj;
+    }
+    const long long dg_stride = dstep * (2 * N3), dn_stride = dstep * (2 * NU);
+    // B operand slots of this unit's three gate rows k = j, n + j, 2n + j
+    unsigned char* b_seq = s_b + (s0 >> 3) * Cfg::SBO_B;
+    const int k1 = NU + jj, k2 = 2 * NU + jj;
+    const int o0 = (jj >> 3) * 128 + (jj & 7) * 2, o1 = (k1 >> 3) * 128 + (k1 & 7) * 2, o2 = (k2 >> 3) * 128 + (k2 & 7) * 2;
+    const uint32_t t_d = t_row + Cfg::TM_D + s0;
+    for (int it = 0; it < T; ++it) {
+      const int step = T - 1 - it;
+      const int stage = it % STAGES;
+      mbar_wait(&in_full[stage], (it / STAGES) & 1);
+      float dprev[SH];
+      if (it > 0) {
+        mbar_wait(d_full, (it - 1) & 1);
+        tc_fence_after();
+        uint32_t dr[SH];
+        tmem_ld8_issue(t_d, dr);
+        tmem_ld8_wait(dr);
+#pragma unroll
+        for (int s = 0; s < SH; ++s) dprev[s] = dhd[s] + __uint_as_float(dr[s]);
+      } else {
+#pragma unroll
+        for (int s = 0; s < SH; ++s) dprev[s] = 0.f;
+      }
+      const float* __restrict__ in = s_in + ((size_t)stage * NSEQ + s0) * ROW + jj;
+      if (unit) {
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
+          const float* row = in + (size_t)s * ROW;
+          const float r = row[0], z = row[NU], nn = row[2 * NU], hnn = row[3 * NU];
+          const float hprev = step > 0 ? row[4 * NU] : 0.f;
+          const float dh = row[5 * NU] + dprev[s];
+          const float dn = dh * (1.f - z);
+          const float dz = dh * (hprev - nn);
+          const float dn_pre = dn * (1.f - nn * nn);
+          const float dz_pre = dz * z * (1.f - z);
+          const float dr_pre = dn_pre * hnn * r * (1.f - r);
+          const float dnr = dn_pre * r;
+          dhd[s] = dh * z;
+          unsigned char* bp = b_seq + s * 16;
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(dr_pre), h1 = __float2bfloat16_rn(dz_pre), h2 = __float2bfloat16_rn(dnr);
+          *reinterpret_cast<__nv_bfloat16*>(bp + o0) = h0;
+          *reinterpret_cast<__nv_bfloat16*>(bp + o1) = h1;
+          *reinterpret_cast<__nv_bfloat16*>(bp + o2) = h2;
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o0) = __float2bfloat16_rn(dr_pre - __bfloat162float(h0));
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o1) = __float2bfloat16_rn(dz_pre - __bfloat162float(h1));
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o2) = __float2bfloat16_rn(dnr - __bfloat162float(h2));
+          if ((valid >> s) & 1u) {
+            float* g = pg[s];
+            g[0] = dr_pre; g[NU] = dz_pre; g[2 * NU] = dn_pre;
+            *pn[s] = dnr;
+          }
+          pg[s] += dg_stride;
+          pn[s] += dn_stride;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(g_full);
+      mbar_arrive(&in_empty[stage]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int NU>
+int launch_bwd_tc(const GruBwdParams& prm, int S, cudaStream_t stream) {
+  using Cfg = TcBwdCfg<NU>;
+  ISA_CUDA(cudaFuncSetAttribute(gru_bwd_tc_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+  dim3 grid((prm.n_seq + S - 1) / S, 2);
+  gru_bwd_tc_kernel<NU><<<grid, Cfg::NT, Cfg::smem_bytes, stream>>>(prm, S);
   return ISA_OK;
 }
 
@@ -1065,6 +1308,12 @@ int isa_gru_scan_bwd(const float* dout, const float* out, const float* stash, co
   prm.dout = dout; prm.out = out; prm.stash = stash; prm.w_hh = w_hh; prm.dgx = dgx; prm.dghn = dghn;
   prm.n_seq = n_seq; prm.T = T; prm.n = n_units;
   prm.map.inner = inner; prm.map.outer_stride = outer_tok_stride; prm.map.inner_stride = inner_tok_stride; prm.map.t_stride = t_tok_stride;
+  if (n_units == 100 && aligned16(stash) && aligned16(out) && aligned16(dout) && !getenv("ISA_GRU_GENERIC") && !getenv("ISA_GRU_REG")) {
+    rc = launch_bwd_tc<100>(prm, pick_S_reg(n_seq, di.num_sms), stream);
+    if (rc) return rc;
+    ISA_CUDA(cudaGetLastError());
+    return ISA_OK;
+  }
   if (n_units == 100 && aligned16(stash) && aligned16(out) && aligned16(dout) && !getenv("ISA_GRU_GENERIC")) {
     switch (pick_S_reg(n_seq, di.num_sms)) {
       case 16: rc = launch_bwd_reg<100, 16>(prm, stream); break;
