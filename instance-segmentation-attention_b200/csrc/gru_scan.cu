@@ -755,19 +755,22 @@ struct TcCfg {
   static constexpr int KP = (NU + 15) / 16 * 16;      // reduction length padded to the MMA's K = 16
   static constexpr int KSTEPS = KP / 16;
   static constexpr int ACOLS = KP / 2;                // TMEM columns of one (gate, part) A tile: packed bf16 pairs
-  static constexpr int TM_D = 6 * ACOLS;              // accumulators: gate g at TM_D + 16 g
+  static constexpr int TM_D = 6 * ACOLS;              // accumulators: chain c, gate g at TM_D + 48 c + 16 g
   static constexpr int NSEQ = 16;                     // MMA N
   static constexpr int SBO_B = (KP / 8) * 128;        // byte stride between 8-sequence groups of the B operand
   static constexpr int B_PART = 2 * SBO_B;            // bytes of one part (hi or lo) of B
   static constexpr int STAGES = 3;
-  static constexpr int NT = 320;                      // warp 0 producer, warp 1 MMA issuer, warps 2..9 gate threads
-  static constexpr int GATE_THREADS = 256;            // (TMEM quarter = warp % 4) x (sequence half = (warp - 2) / 4)
+  // Two independent chains of 8 sequences each (every MMA still spans all N = 16 columns; a chain reads back only its
+  // own columns of its own accumulators): while one chain's MMAs and hand-offs are in flight the other chain's gate
+  // threads compute, so neither the gate math nor the tensor pipe waits for the other.
+  static constexpr int NT = 640;                      // warp 0 producer, warps 1-2 MMA issuers, warp 3 idle, warps 4..19 gate threads
+  static constexpr int CHAIN_THREADS = 256;           // per chain: (TMEM quarter = warp % 4) x (4-sequence half)
   static constexpr size_t gx_bytes = (size_t)STAGES * NSEQ * 3 * NU * sizeof(float);
   static constexpr size_t used_bytes = gx_bytes + 2 * B_PART + 16 * 8 + NSEQ * 8 + 16 + 128;
   // the CTA allocates all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs can never
   // share an SM (the second one would spin in tcgen05.alloc until the first retires)
   static constexpr size_t smem_bytes = used_bytes > 120 * 1024 ? used_bytes : 120 * 1024;
-  static_assert(TM_D + 3 * 16 <= 512 && NU <= 128 && NU % 4 == 0, "unsupported width");
+  static_assert(TM_D + 2 * 3 * 16 <= 512 && NU <= 128 && NU % 4 == 0, "unsupported width");
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * x)); }
@@ -786,8 +789,8 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tok + NSEQ);
   uint64_t* gx_full = s_bar;
   uint64_t* gx_empty = s_bar + STAGES;
-  uint64_t* h_full = s_bar + 2 * STAGES;
-  uint64_t* d_full = s_bar + 2 * STAGES + 1;
+  uint64_t* h_full = s_bar + 2 * STAGES;          // [2] per chain
+  uint64_t* d_full = s_bar + 2 * STAGES + 2;      // [2]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int d = blockIdx.y;
@@ -796,9 +799,8 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
   const int n_valid = min(S, prm.n_seq - q0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&gx_full[i], 1); mbar_init(&gx_empty[i], Cfg::GATE_THREADS); }
-    mbar_init(h_full, Cfg::GATE_THREADS);
-    mbar_init(d_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&gx_full[i], 1); mbar_init(&gx_empty[i], 2 * Cfg::CHAIN_THREADS); }
+    for (int c = 0; c < 2; ++c) { mbar_init(&h_full[c], Cfg::CHAIN_THREADS); mbar_init(&d_full[c], 1); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < (int)((Cfg::gx_bytes + 2 * Cfg::B_PART) / 4); i += Cfg::NT) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
   const int quarter = warp & 3;
   const int j = quarter * 32 + lane;                       // hidden unit of a gate thread = TMEM lane
   const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-  if (warp >= 2) {
+  if (warp >= 4 && warp < 8) {
     // W_hh -> TMEM (once): row j of gate g, split into bf16 hi / lo, two values per 32-bit column
     const float* __restrict__ wsrc = prm.w_hh + (size_t)d * N3 * NU;
 #pragma unroll 1
@@ -854,33 +856,39 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
         tma_bulk_g2s(s_gx + ((size_t)stage * NSEQ + lane) * N3, prm.gx + ((size_t)tok * 2 + d) * N3, N3 * 4u, &gx_full[stage]);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform, one elected lane) =====================
+  } else if (warp <= 2) {
+    // ===================== MMA issuer of chain c = warp - 1 (warp-uniform, one elected lane) =====================
+    const int c = warp - 1;
     const uint32_t el = elect_one();
     constexpr uint32_t idesc = make_idesc(128, NSEQ);
     const uint64_t b_hi = make_desc(smem_u32(s_b), 128, Cfg::SBO_B);
     const uint64_t b_lo = make_desc(smem_u32(s_b + Cfg::B_PART), 128, Cfg::SBO_B);
     for (int step = 0; step < T; ++step) {
-      if (step > 0) mbar_wait(h_full, (step - 1) & 1);
+      if (step > 0) mbar_wait(&h_full[c], (step - 1) & 1);
       tc_fence_after();
+      // consecutive MMAs go to different accumulators (gates): back-to-back accumulations into the SAME TMEM tile would
+      // serialise on the tensor pipe's latency, far above the 8 cycles an N = 16 MMA occupies it
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        const uint32_t dcol = tmem + Cfg::TM_D + g * 16;
+      for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
+        const uint32_t ko = (kk * 256) >> 4;
 #pragma unroll
-        for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
-          const uint32_t a_hi = tmem + (g * 2) * Cfg::ACOLS + kk * 8, a_lo = tmem + (g * 2 + 1) * Cfg::ACOLS + kk * 8;
-          const uint32_t ko = (kk * 256) >> 4;
-          umma_bf16_ts_e(el, dcol, a_hi, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
-          umma_bf16_ts_e(el, dcol, a_hi, b_lo + ko, idesc, 1u);
-          umma_bf16_ts_e(el, dcol, a_lo, b_hi + ko, idesc, 1u);
+        for (int term = 0; term < 3; ++term) {
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const uint32_t dcol = tmem + Cfg::TM_D + c * 48 + g * 16;
+            const uint32_t a = tmem + (g * 2 + (term == 2 ? 1 : 0)) * Cfg::ACOLS + kk * 8;
+            umma_bf16_ts_e(el, dcol, a, (term == 1 ? b_lo : b_hi) + ko, idesc, (kk > 0 || term > 0) ? 1u : 0u);
+          }
         }
       }
-      umma_commit_e(el, d_full);
+      umma_commit_e(el, &d_full[c]);
     }
-  } else {
-    // ===================== gate threads: unit j, eight sequences (two warps share a TMEM quarter) =====================
-    constexpr int SH = NSEQ / 2;
-    const int s0 = ((warp - 2) >> 2) * SH;                 // first sequence of this thread
+  } else if (warp >= 4) {
+    // ===================== gate threads: unit j, four sequences of chain c =====================
+    constexpr int SH = 4;
+    const int sub = (warp - 4) >> 2;                       // 0..3
+    const int c = sub >> 1;
+    const int s0 = c * 8 + (sub & 1) * SH;                 // first sequence of this thread
     const bool unit = j < NU;
     const int jj = unit ? j : 0;
     const float bhr = __ldg(prm.b_hh + d * N3 + jj) + (prm.b_ih ? __ldg(prm.b_ih + d * N3 + jj) : 0.f);
@@ -905,51 +913,73 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
     }
     const long long dout = dstep * (2 * NU), dstash = dstep * (8 * NU);
     const bool has_stash = prm.stash != nullptr;
-    unsigned char* b_base = s_b + (jj >> 3) * 128 + (jj & 7) * 2 + (s0 >> 3) * Cfg::SBO_B;
-    const uint32_t t_d = t_row + Cfg::TM_D + s0;
+    // sequence s0 + s: row group (s0 + s) / 8 = c, row (s0 + s) % 8 inside the core matrices
+    unsigned char* b_base = s_b + (jj >> 3) * 128 + (jj & 7) * 2 + c * Cfg::SBO_B + (s0 & 7) * 16;
+    const uint32_t t_d = t_row + Cfg::TM_D + c * 48 + s0;
     for (int step = 0; step < T; ++step) {
       const int stage = step % STAGES;
-      mbar_wait(d_full, step & 1);
+      mbar_wait(&d_full[c], step & 1);
       tc_fence_after();
       uint32_t ar[SH], az[SH], an[SH];
-      tmem_ld8_issue(t_d, ar);
-      tmem_ld8_issue(t_d + 16, az);
-      tmem_ld8_issue(t_d + 32, an);
-      tmem_ld8_wait(ar);
-      tmem_ld8_wait(az);
-      tmem_ld8_wait(an);
+      tmem_ld4_issue(t_d, ar);
+      tmem_ld4_issue(t_d + 16, az);
+      tmem_ld4_issue(t_d + 32, an);
+      tmem_ld4_wait(ar);
+      tmem_ld4_wait(az);
+      tmem_ld4_wait(an);
       mbar_wait(&gx_full[stage], (step / STAGES) & 1);
       const float* __restrict__ gxs = s_gx + ((size_t)stage * NSEQ + s0) * N3 + jj;
+      float hn[SH], r[SH], z[SH], nn[SH];
+      if (unit) {
+        // staged over the thread's sequences so that the four dependent MUFU chains run interleaved, not one after another
+        constexpr float kL2E = 1.4426950408889634f;
+        float pr[SH], pz[SH], pn[SH];
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
+          pr[s] = gxs[s * N3] + __uint_as_float(ar[s]) + bhr;
+          pz[s] = gxs[s * N3 + NU] + __uint_as_float(az[s]) + bhz;
+          pn[s] = gxs[s * N3 + 2 * NU] + bin;
+          hn[s] = __uint_as_float(an[s]) + bhn;
+        }
+#pragma unroll
+        for (int s = 0; s < SH; ++s) { pr[s] = ex2_approx(-kL2E * pr[s]); pz[s] = ex2_approx(-kL2E * pz[s]); }
+#pragma unroll
+        for (int s = 0; s < SH; ++s) { r[s] = __fdividef(1.f, 1.f + pr[s]); z[s] = __fdividef(1.f, 1.f + pz[s]); }
+#pragma unroll
+        for (int s = 0; s < SH; ++s) pn[s] = ex2_approx(-2.f * kL2E * fmaf(r[s], hn[s], pn[s]));
+#pragma unroll
+        for (int s = 0; s < SH; ++s) nn[s] = fmaf(2.f, __fdividef(1.f, 1.f + pn[s]), -1.f);
+#pragma unroll
+        for (int s = 0; s < SH; ++s) hreg[s] = fmaf(z[s], hreg[s] - nn[s], nn[s]);        // (1 - z) n + z h
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
+          const __nv_bfloat16 hh = __float2bfloat16_rn(hreg[s]);
+          const __nv_bfloat16 hl = __float2bfloat16_rn(hreg[s] - __bfloat162float(hh));
+          unsigned char* bp = b_base + s * 16;
+          *reinterpret_cast<__nv_bfloat16*>(bp) = hh;
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART) = hl;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();          // B operand writes -> visible to the tensor core's async proxy
+      mbar_arrive(&h_full[c]);
+      mbar_arrive(&gx_empty[stage]);
+      // global stores AFTER the hand-off: mbarrier.arrive has release semantics, so stores issued before it would have
+      // to be acknowledged (~1 k cycles) before the next step's MMAs could start; here they drain under the MMAs
       if (unit) {
 #pragma unroll
         for (int s = 0; s < SH; ++s) {
-          const float xr = gxs[s * N3], xz = gxs[s * N3 + NU], xn = gxs[s * N3 + 2 * NU];
-          const float hn = __uint_as_float(an[s]) + bhn;
-          const float r = sigmoid_fast(xr + __uint_as_float(ar[s]) + bhr);
-          const float z = sigmoid_fast(xz + __uint_as_float(az[s]) + bhz);
-          const float nn = tanh_fast(xn + bin + r * hn);
-          const float hnew = fmaf(z, hreg[s] - nn, nn);          // (1 - z) n + z h
-          hreg[s] = hnew;
-          const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
-          const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
-          unsigned char* bp = b_base + s * 16;                   // SH = 8 sequences = one core-matrix row group
-          *reinterpret_cast<__nv_bfloat16*>(bp) = hh;
-          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART) = hl;
           if ((valid >> s) & 1u) {
-            *po[s] = hnew;
+            *po[s] = hreg[s];
             if (has_stash) {
               float* st4 = ps[s];
-              st4[0] = r; st4[NU] = z; st4[2 * NU] = nn; st4[3 * NU] = hn;
+              st4[0] = r[s]; st4[NU] = z[s]; st4[2 * NU] = nn[s]; st4[3 * NU] = hn[s];
             }
           }
           po[s] += dout;
           ps[s] += dstash;
         }
       }
-      tc_fence_before();
-      fence_proxy_async();          // B operand writes -> visible to the tensor core's async proxy
-      mbar_arrive(h_full);
-      mbar_arrive(&gx_empty[stage]);
     }
   }
   tc_fence_before();
@@ -983,12 +1013,12 @@ struct TcBwdCfg {
   static constexpr int B_PART = 2 * SBO_B;
   static constexpr int STAGES = 3;
   static constexpr int ROW = 6 * NU;                  // floats per sequence and stage: stash 4n | h_prev n | dout n
-  static constexpr int NT = 320;
-  static constexpr int GATE_THREADS = 256;
+  static constexpr int NT = 640;                      // same roles and two-chain organisation as the forward kernel
+  static constexpr int CHAIN_THREADS = 256;
   static constexpr size_t in_bytes = (size_t)STAGES * NSEQ * ROW * sizeof(float);
   static constexpr size_t used_bytes = in_bytes + 2 * B_PART + 16 * 8 + NSEQ * 8 + 16 + 128;
   static constexpr size_t smem_bytes = used_bytes > 120 * 1024 ? used_bytes : 120 * 1024;
-  static_assert(TM_D + 16 <= 512 && NU <= 128 && NU % 4 == 0, "unsupported width");
+  static_assert(TM_D + 2 * 16 <= 512 && NU <= 128 && NU % 4 == 0, "unsupported width");
 };
 
 template <int NU>
@@ -1004,8 +1034,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tok + NSEQ);
   uint64_t* in_full = s_bar;
   uint64_t* in_empty = s_bar + STAGES;
-  uint64_t* g_full = s_bar + 2 * STAGES;
-  uint64_t* d_full = s_bar + 2 * STAGES + 1;
+  uint64_t* g_full = s_bar + 2 * STAGES;          // [2] per chain
+  uint64_t* d_full = s_bar + 2 * STAGES + 2;      // [2]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int d = blockIdx.y;
@@ -1014,9 +1044,8 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
   const int n_valid = min(S, prm.n_seq - q0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], Cfg::GATE_THREADS); }
-    mbar_init(g_full, Cfg::GATE_THREADS);
-    mbar_init(d_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 2 * Cfg::CHAIN_THREADS); }
+    for (int c = 0; c < 2; ++c) { mbar_init(&g_full[c], Cfg::CHAIN_THREADS); mbar_init(&d_full[c], 1); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < (int)((Cfg::in_bytes + 2 * Cfg::B_PART) / 4); i += Cfg::NT) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
@@ -1031,7 +1060,7 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
   const int quarter = warp & 3;
   const int j = quarter * 32 + lane;
   const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-  if (warp >= 2 && warp < 6) {
+  if (warp >= 4 && warp < 8) {
     // W_hh^T -> TMEM (once): row u = j holds W_hh[g][u] over g, bf16 hi / lo pairs (coalesced: lanes run along u)
     const float* __restrict__ wsrc = prm.w_hh + (size_t)d * N3 * NU;
 #pragma unroll 1
@@ -1076,29 +1105,33 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
         tma_bulk_g2s(dst + 5 * NU, prm.dout + (size_t)tok * (2 * NU) + d * NU, NU * 4u, &in_full[stage]);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp <= 2) {
+    // ===================== MMA issuer of chain c = warp - 1 =====================
+    const int c = warp - 1;
     const uint32_t el = elect_one();
     constexpr uint32_t idesc = make_idesc(128, NSEQ);
     const uint64_t b_hi = make_desc(smem_u32(s_b), 128, Cfg::SBO_B);
     const uint64_t b_lo = make_desc(smem_u32(s_b + Cfg::B_PART), 128, Cfg::SBO_B);
+    const uint32_t dcol = tmem + Cfg::TM_D + c * 16;
     for (int it = 0; it + 1 < T; ++it) {                 // the last step's dh_{-1} is not needed
-      mbar_wait(g_full, it & 1);
+      mbar_wait(&g_full[c], it & 1);
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
         const uint32_t a_hi = tmem + kk * 8, a_lo = tmem + Cfg::ACOLS + kk * 8;
         const uint32_t ko = (kk * 256) >> 4;
-        umma_bf16_ts_e(el, tmem + Cfg::TM_D, a_hi, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
-        umma_bf16_ts_e(el, tmem + Cfg::TM_D, a_hi, b_lo + ko, idesc, 1u);
-        umma_bf16_ts_e(el, tmem + Cfg::TM_D, a_lo, b_hi + ko, idesc, 1u);
+        umma_bf16_ts_e(el, dcol, a_hi, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
+        umma_bf16_ts_e(el, dcol, a_hi, b_lo + ko, idesc, 1u);
+        umma_bf16_ts_e(el, dcol, a_lo, b_hi + ko, idesc, 1u);
       }
-      umma_commit_e(el, d_full);
+      umma_commit_e(el, &d_full[c]);
     }
-  } else {
-    // ===================== gate threads: unit j, eight sequences =====================
-    constexpr int SH = NSEQ / 2;
-    const int s0 = ((warp - 2) >> 2) * SH;
+  } else if (warp >= 4) {
+    // ===================== gate threads: unit j, four sequences of chain c =====================
+    constexpr int SH = 4;
+    const int sub = (warp - 4) >> 2;
+    const int c = sub >> 1;
+    const int s0 = c * 8 + (sub & 1) * SH;
     const bool unit = j < NU;
     const int jj = unit ? j : 0;
     float dhd[SH];
@@ -1118,21 +1151,21 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
     }
     const long long dg_stride = dstep * (2 * N3), dn_stride = dstep * (2 * NU);
     // B operand slots of this unit's three gate rows k = j, n + j, 2n + j
-    unsigned char* b_seq = s_b + (s0 >> 3) * Cfg::SBO_B;
+    unsigned char* b_seq = s_b + c * Cfg::SBO_B + (s0 & 7) * 16;
     const int k1 = NU + jj, k2 = 2 * NU + jj;
     const int o0 = (jj >> 3) * 128 + (jj & 7) * 2, o1 = (k1 >> 3) * 128 + (k1 & 7) * 2, o2 = (k2 >> 3) * 128 + (k2 & 7) * 2;
-    const uint32_t t_d = t_row + Cfg::TM_D + s0;
+    const uint32_t t_d = t_row + Cfg::TM_D + c * 16 + s0;
     for (int it = 0; it < T; ++it) {
       const int step = T - 1 - it;
       const int stage = it % STAGES;
       mbar_wait(&in_full[stage], (it / STAGES) & 1);
       float dprev[SH];
       if (it > 0) {
-        mbar_wait(d_full, (it - 1) & 1);
+        mbar_wait(&d_full[c], (it - 1) & 1);
         tc_fence_after();
         uint32_t dr[SH];
-        tmem_ld8_issue(t_d, dr);
-        tmem_ld8_wait(dr);
+        tmem_ld4_issue(t_d, dr);
+        tmem_ld4_wait(dr);
 #pragma unroll
         for (int s = 0; s < SH; ++s) dprev[s] = dhd[s] + __uint_as_float(dr[s]);
       } else {
@@ -1140,41 +1173,56 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
         for (int s = 0; s < SH; ++s) dprev[s] = 0.f;
       }
       const float* __restrict__ in = s_in + ((size_t)stage * NSEQ + s0) * ROW + jj;
+      float dn_pre[SH], dz_pre[SH], dr_pre[SH], dnr[SH];
       if (unit) {
+        // staged over the thread's sequences (loads, then arithmetic, then stores) for instruction-level parallelism
+        float r[SH], z[SH], nn[SH], hnn[SH], hp[SH], dh[SH];
 #pragma unroll
         for (int s = 0; s < SH; ++s) {
           const float* row = in + (size_t)s * ROW;
-          const float r = row[0], z = row[NU], nn = row[2 * NU], hnn = row[3 * NU];
-          const float hprev = step > 0 ? row[4 * NU] : 0.f;
-          const float dh = row[5 * NU] + dprev[s];
-          const float dn = dh * (1.f - z);
-          const float dz = dh * (hprev - nn);
-          const float dn_pre = dn * (1.f - nn * nn);
-          const float dz_pre = dz * z * (1.f - z);
-          const float dr_pre = dn_pre * hnn * r * (1.f - r);
-          const float dnr = dn_pre * r;
-          dhd[s] = dh * z;
+          r[s] = row[0]; z[s] = row[NU]; nn[s] = row[2 * NU]; hnn[s] = row[3 * NU];
+          hp[s] = step > 0 ? row[4 * NU] : 0.f;
+          dh[s] = row[5 * NU] + dprev[s];
+        }
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
+          const float dn = dh[s] * (1.f - z[s]);
+          const float dz = dh[s] * (hp[s] - nn[s]);
+          dn_pre[s] = dn * (1.f - nn[s] * nn[s]);
+          dz_pre[s] = dz * z[s] * (1.f - z[s]);
+          dr_pre[s] = dn_pre[s] * hnn[s] * r[s] * (1.f - r[s]);
+          dnr[s] = dn_pre[s] * r[s];
+          dhd[s] = dh[s] * z[s];
+        }
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
           unsigned char* bp = b_seq + s * 16;
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(dr_pre), h1 = __float2bfloat16_rn(dz_pre), h2 = __float2bfloat16_rn(dnr);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(dr_pre[s]), h1 = __float2bfloat16_rn(dz_pre[s]), h2 = __float2bfloat16_rn(dnr[s]);
           *reinterpret_cast<__nv_bfloat16*>(bp + o0) = h0;
           *reinterpret_cast<__nv_bfloat16*>(bp + o1) = h1;
           *reinterpret_cast<__nv_bfloat16*>(bp + o2) = h2;
-          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o0) = __float2bfloat16_rn(dr_pre - __bfloat162float(h0));
-          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o1) = __float2bfloat16_rn(dz_pre - __bfloat162float(h1));
-          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o2) = __float2bfloat16_rn(dnr - __bfloat162float(h2));
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o0) = __float2bfloat16_rn(dr_pre[s] - __bfloat162float(h0));
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o1) = __float2bfloat16_rn(dz_pre[s] - __bfloat162float(h1));
+          *reinterpret_cast<__nv_bfloat16*>(bp + Cfg::B_PART + o2) = __float2bfloat16_rn(dnr[s] - __bfloat162float(h2));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(&g_full[c]);
+      mbar_arrive(&in_empty[stage]);
+      // global stores after the hand-off (see the forward kernel)
+      if (unit) {
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
           if ((valid >> s) & 1u) {
             float* g = pg[s];
-            g[0] = dr_pre; g[NU] = dz_pre; g[2 * NU] = dn_pre;
-            *pn[s] = dnr;
+            g[0] = dr_pre[s]; g[NU] = dz_pre[s]; g[2 * NU] = dn_pre[s];
+            *pn[s] = dnr[s];
           }
           pg[s] += dg_stride;
           pn[s] += dn_stride;
         }
       }
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(g_full);
-      mbar_arrive(&in_empty[stage]);
     }
   }
   tc_fence_before();
