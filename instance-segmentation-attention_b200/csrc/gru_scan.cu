@@ -759,7 +759,7 @@ struct TcCfg {
   static constexpr int NSEQ = 16;                     // MMA N
   static constexpr int SBO_B = (KP / 8) * 128;        // byte stride between 8-sequence groups of the B operand
   static constexpr int B_PART = 2 * SBO_B;            // bytes of one part (hi or lo) of B
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 5;
   // Two independent chains of 8 sequences each (every MMA still spans all N = 16 columns; a chain reads back only its
   // own columns of its own accumulators): while one chain's MMAs and hand-offs are in flight the other chain's gate
   // threads compute, so neither the gate math nor the tensor pipe waits for the other.
@@ -815,13 +815,14 @@ __global__ void __launch_bounds__(TcCfg<NU>::NT, 1) gru_fwd_tc_kernel(const GruF
   const int quarter = warp & 3;
   const int j = quarter * 32 + lane;                       // hidden unit of a gate thread = TMEM lane
   const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-  if (warp >= 4 && warp < 8) {
-    // W_hh -> TMEM (once): row j of gate g, split into bf16 hi / lo, two values per 32-bit column
+  if (warp >= 4) {
+    // W_hh -> TMEM (once): row j of gate g, split into bf16 hi / lo, two values per 32-bit column; the (gate, k-chunk)
+    // items are dealt round-robin to the four warps that share a TMEM quarter
     const float* __restrict__ wsrc = prm.w_hh + (size_t)d * N3 * NU;
 #pragma unroll 1
-    for (int g = 0; g < 3; ++g) {
-#pragma unroll 1
-      for (int c = 0; c < Cfg::KSTEPS; ++c) {
+    for (int item = (warp - 4) >> 2; item < 3 * Cfg::KSTEPS; item += 4) {
+      const int g = item / Cfg::KSTEPS, c = item % Cfg::KSTEPS;
+      {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -1011,7 +1012,7 @@ struct TcBwdCfg {
   static constexpr int NSEQ = 16;
   static constexpr int SBO_B = (KP / 8) * 128;
   static constexpr int B_PART = 2 * SBO_B;
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 4;
   static constexpr int ROW = 6 * NU;                  // floats per sequence and stage: stash 4n | h_prev n | dout n
   static constexpr int NT = 640;                      // same roles and two-chain organisation as the forward kernel
   static constexpr int CHAIN_THREADS = 256;
@@ -1060,11 +1061,12 @@ __global__ void __launch_bounds__(TcBwdCfg<NU>::NT, 1) gru_bwd_tc_kernel(const G
   const int quarter = warp & 3;
   const int j = quarter * 32 + lane;
   const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
-  if (warp >= 4 && warp < 8) {
-    // W_hh^T -> TMEM (once): row u = j holds W_hh[g][u] over g, bf16 hi / lo pairs (coalesced: lanes run along u)
+  if (warp >= 4) {
+    // W_hh^T -> TMEM (once): row u = j holds W_hh[g][u] over g, bf16 hi / lo pairs (coalesced: lanes run along u); the
+    // k-chunks are dealt round-robin to the four warps that share a TMEM quarter
     const float* __restrict__ wsrc = prm.w_hh + (size_t)d * N3 * NU;
 #pragma unroll 1
-    for (int c = 0; c < Cfg::KSTEPS; ++c) {
+    for (int c = (warp - 4) >> 2; c < Cfg::KSTEPS; c += 4) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
