@@ -36,13 +36,12 @@ namespace {
 constexpr int kTileQ = 128;
 constexpr int kTileK = 128;
 constexpr int kDP = 16;            // padded head width
-constexpr int kStages = 2;
 constexpr int kOperandBytes = kTileQ * kDP * 2;     // 4096: one bf16 [128][16] operand tile
 constexpr int kKvTileBytes = 4 * kOperandBytes;     // Kh | Kl | Vh^T | Vl^T
 constexpr int kQTileBytes = 2 * kOperandBytes;      // Qh | Ql
-constexpr int kPBytes = kTileQ * kTileK * 2;        // 32768: one bf16 [128][128] operand
 constexpr int kFwdThreads = 192;
-constexpr int kTmemCols = 256;                      // S: [0,128), O: [128,144)
+constexpr int kTmemCols = 256;                      // S / P: [0,128), O: [128,160) = [P V_hi | P V_lo]
+constexpr int kFwdStages = 4;
 constexpr int kBwdThreads = 384;                    // warp 0 producer, warps 1-2 MMA issuers (even / odd sub-tiles), warp 3 idle, warps 4..11 math
 constexpr int kBwdTmemCols = 512;
 constexpr int kTmemO = 128;
@@ -161,11 +160,9 @@ struct FwdParams {
 
 struct FwdSmem {
   unsigned char q[kQTileBytes];
-  unsigned char kv[kStages][kKvTileBytes];
-  unsigned char p_hi[kPBytes];
-  unsigned char p_lo[kPBytes];
+  unsigned char kv[kFwdStages][kKvTileBytes];
   uint64_t q_full, s_full, p_full, o_full;
-  uint64_t kv_full[kStages], kv_empty[kStages];
+  uint64_t kv_full[kFwdStages], kv_empty[kFwdStages];
   uint32_t tmem_base;
 };
 
@@ -187,34 +184,40 @@ __device__ __forceinline__ float fwd_tile_max(uint32_t t_row, const uint32_t (&b
   }
   return m;
 }
+// exp pass: P = exp2(S - m) goes back into TENSOR MEMORY as the A operand of the PV MMAs, written over the 32 S
+// columns this thread has just read: [P hi: 16 packed columns | P lo: 16 packed columns] per 32-key chunk
 template <bool MASKED>
-__device__ __forceinline__ float fwd_tile_exp(uint32_t t_row, const uint32_t (&bits)[4], float m_safe, unsigned char* p_hi, unsigned char* p_lo, int r) {
-  float l = 0.f;
+__device__ __forceinline__ float fwd_tile_exp(uint32_t t_row, const uint32_t (&bits)[4], float m_safe) {
+  float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
-    float s[32];
-    tmem_ld32(t_row + c * 32, s);
+    uint32_t sr[32];
+    tmem_ld32_issue(t_row + c * 32, sr);
+    tmem_ld32_wait(sr);
+    uint32_t ph[16], pl[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float pv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = g * 8 + e;
-        float p = ex2_approx(s[i] - m_safe);
-        if (MASKED && ((bits[c] >> i) & 1u)) p = 0.f;
-        pv[e] = p;
-        l += p;
+    for (int i = 0; i < 32; i += 2) {
+      float p0 = ex2_approx(__uint_as_float(sr[i]) - m_safe);
+      float p1 = ex2_approx(__uint_as_float(sr[i + 1]) - m_safe);
+      if (MASKED) {
+        if ((bits[c] >> i) & 1u) p0 = 0.f;
+        if ((bits[c] >> (i + 1)) & 1u) p1 = 0.f;
       }
-      store_group(p_hi, p_lo, kmajor_off(r, c * 32 + g * 8, kSboP), pv);
+      l0 += p0;
+      l1 += p1;
+      split2(p0, p1, ph[i >> 1], pl[i >> 1]);
     }
+    tmem_st16_issue(t_row + c * 32, ph);
+    tmem_st16_issue(t_row + c * 32 + 16, pl);
   }
-  return l;
+  tmem_st_wait();
+  return l0 + l1;
 }
 
 __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int qt = blockIdx.x, bh = blockIdx.y;
   const int nKt = prm.nKt;
 
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
     mbar_init(&sm.s_full, 1);
     mbar_init(&sm.p_full, 128);
     mbar_init(&sm.o_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
+    for (int s = 0; s < kFwdStages; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&sm.tmem_base, kTmemCols);
@@ -238,44 +241,46 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
       mbar_arrive_expect_tx(&sm.q_full, kQTileBytes);
       tma_bulk_g2s(sm.q, prm.qblk + ((size_t)bh * prm.nQt + qt) * kQTileBytes, kQTileBytes, &sm.q_full);
       for (int j = 0; j < nKt; ++j) {
-        const int st = j % kStages;
-        mbar_wait(&sm.kv_empty[st], ((j / kStages) & 1) ^ 1);
+        const int st = j % kFwdStages;
+        mbar_wait(&sm.kv_empty[st], ((j / kFwdStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&sm.kv_full[st], kKvTileBytes);
         tma_bulk_g2s(sm.kv[st], prm.kvblk + ((size_t)bh * nKt + j) * kKvTileBytes, kKvTileBytes, &sm.kv_full[st]);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one elected lane) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform code, one elected lane executes the instructions =====================
+    {
+      const uint32_t el = elect_one();
       constexpr uint32_t idesc_s = make_idesc(kTileQ, kTileK);
-      constexpr uint32_t idesc_o = make_idesc(kTileQ, kDP);
-      const uint32_t q_hi = smem_u32(sm.q), q_lo = q_hi + kOperandBytes;
-      const uint32_t p_hi = smem_u32(sm.p_hi), p_lo = smem_u32(sm.p_lo);
+      constexpr uint32_t idesc_o2 = make_idesc(kTileQ, 2 * kDP);   // P_hi x [V_hi ; V_lo] -> 32 columns
+      constexpr uint32_t idesc_o1 = make_idesc(kTileQ, kDP);
+      const uint64_t q_hi = make_desc(smem_u32(sm.q), 128, kSboQK), q_lo = q_hi + (kOperandBytes >> 4);
+      const uint64_t k0 = make_desc(smem_u32(sm.kv[0]), 128, kSboQK);      // K operands of stage 0
+      const uint64_t v0 = make_desc(smem_u32(sm.kv[0]) + 2 * kOperandBytes, 128, kSboP);   // V^T operands of stage 0
       mbar_wait(&sm.q_full, 0);
       for (int j = 0; j < nKt; ++j) {
-        const int st = j % kStages;
-        const uint32_t kvb = smem_u32(sm.kv[st]);
-        mbar_wait(&sm.kv_full[st], (j / kStages) & 1);
+        const int st = j % kFwdStages;
+        const uint64_t kd = k0 + (uint32_t)st * (kKvTileBytes >> 4), vd = v0 + (uint32_t)st * (kKvTileBytes >> 4);
+        mbar_wait(&sm.kv_full[st], (j / kFwdStages) & 1);
         tc_fence_after();
         // S = Qh Kh^T + Qh Kl^T + Ql Kh^T
-        umma_bf16(tmem, make_desc(q_hi, 128, kSboQK), make_desc(kvb, 128, kSboQK), idesc_s, 0);
-        umma_bf16(tmem, make_desc(q_hi, 128, kSboQK), make_desc(kvb + kOperandBytes, 128, kSboQK), idesc_s, 1);
-        umma_bf16(tmem, make_desc(q_lo, 128, kSboQK), make_desc(kvb, 128, kSboQK), idesc_s, 1);
-        umma_commit(&sm.s_full);
-        // O += Ph Vh + Ph Vl + Pl Vh   (P written by the softmax warps)
+        umma_bf16_e(el, tmem, q_hi, kd, idesc_s, 0);
+        umma_bf16_e(el, tmem, q_hi, kd + (kOperandBytes >> 4), idesc_s, 1);
+        umma_bf16_e(el, tmem, q_lo, kd, idesc_s, 1);
+        umma_commit_e(el, &sm.s_full);
+        // O += Ph [Vh ; Vl] + Pl Vh, P read from tensor memory (written over S by the softmax warps)
         mbar_wait(&sm.p_full, j & 1);
         tc_fence_after();
-        const uint32_t vh = kvb + 2 * kOperandBytes, vl = kvb + 3 * kOperandBytes;
 #pragma unroll
         for (int kk = 0; kk < kTileK / 16; ++kk) {
-          const uint32_t ko = kk * 256;
-          umma_bf16(tmem + kTmemO, make_desc(p_hi + ko, 128, kSboP), make_desc(vh + ko, 128, kSboP), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-          umma_bf16(tmem + kTmemO, make_desc(p_hi + ko, 128, kSboP), make_desc(vl + ko, 128, kSboP), idesc_o, 1);
-          umma_bf16(tmem + kTmemO, make_desc(p_lo + ko, 128, kSboP), make_desc(vh + ko, 128, kSboP), idesc_o, 1);
+          const uint32_t ca = (kk >> 1) * 32 + (kk & 1) * 8;
+          const uint32_t ko = (kk * 256) >> 4;
+          umma_bf16_ts_e(el, tmem + kTmemO, tmem + ca, vd + ko, idesc_o2, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts_e(el, tmem + kTmemO, tmem + ca + 16, vd + ko, idesc_o1, 1);
         }
-        umma_commit(&sm.kv_empty[st]);
+        umma_commit_e(el, &sm.kv_empty[st]);
       }
-      umma_commit(&sm.o_full);
+      umma_commit_e(el, &sm.o_full);
     }
   } else {
     // ===================== softmax / correction / epilogue: one query row per thread =====================
@@ -295,28 +300,32 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
       const float m_new = fmaxf(m_run, m_tile);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
-      const float l_tile = masked ? fwd_tile_exp<true>(t_row, bits, m_safe, sm.p_hi, sm.p_lo, r)
-                                  : fwd_tile_exp<false>(t_row, bits, m_safe, sm.p_hi, sm.p_lo, r);
+      const float l_tile = masked ? fwd_tile_exp<true>(t_row, bits, m_safe) : fwd_tile_exp<false>(t_row, bits, m_safe);
       l_run = l_run * alpha + l_tile;
       // rescale the running output (previous PV MMAs are complete: s_full was committed after them).
       // tcgen05.ld/st are warp-collective (.sync.aligned): the branch must be warp-uniform
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        float o[16];
-        tmem_ld16(t_row + kTmemO, o);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] *= alpha;
-        tmem_st16(t_row + kTmemO, o);
+        for (int h = 0; h < 2; ++h) {          // both halves of the accumulator: P V_hi and P V_lo
+          float o[16];
+          tmem_ld16(t_row + kTmemO + h * 16, o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] *= alpha;
+          tmem_st16(t_row + kTmemO + h * 16, o);
+        }
       }
       m_run = m_new;
-      fence_proxy_async();   // generic-proxy smem writes (P) -> visible to the tensor core's async proxy
       tc_fence_before();
       mbar_arrive(&sm.p_full);
     }
     // epilogue
     mbar_wait(&sm.o_full, 0);
     tc_fence_after();
-    float o[16];
+    float o[16], o2[16];
     tmem_ld16(t_row + kTmemO, o);
+    tmem_ld16(t_row + kTmemO + 16, o2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] += o2[i];
     if (row < prm.Lq) {
       const float inv = 1.f / l_run;   // fully masked row: 0 * inf = NaN, like softmax over all -inf
       float* dst = prm.out + ((size_t)bh * prm.Lq + row) * prm.dv;
