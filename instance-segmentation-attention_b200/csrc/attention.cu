@@ -42,6 +42,10 @@ constexpr int kQTileBytes = 2 * kOperandBytes;      // Qh | Ql
 constexpr int kFwdThreads = 192;
 constexpr int kTmemCols = 256;                      // S / P: [0,128), O: [128,160) = [P V_hi | P V_lo]
 constexpr int kFwdStages = 4;
+// The tensor core adds into its fp32 accumulator with truncation, so thousands of same-sign accumulations drift
+// (measured -9e-4 relative at L = 131 072 keys).  Every kFlushTiles key tiles the PV accumulator is therefore folded
+// into fp32 registers (round-to-nearest adds) and restarted.
+constexpr int kFlushTiles = 16;
 constexpr int kBwdThreads = 384;                    // warp 0 producer, warps 1-2 MMA issuers (even / odd sub-tiles), warp 3 idle, warps 4..11 math
 constexpr int kBwdTmemCols = 512;
 constexpr int kTmemO = 128;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
         for (int kk = 0; kk < kTileK / 16; ++kk) {
           const uint32_t ca = (kk >> 1) * 32 + (kk & 1) * 8;
           const uint32_t ko = (kk * 256) >> 4;
-          umma_bf16_ts_e(el, tmem + kTmemO, tmem + ca, vd + ko, idesc_o2, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts_e(el, tmem + kTmemO, tmem + ca, vd + ko, idesc_o2, (j % kFlushTiles != 0 || kk > 0) ? 1u : 0u);
           umma_bf16_ts_e(el, tmem + kTmemO, tmem + ca + 16, vd + ko, idesc_o1, 1);
         }
         umma_commit_e(el, &sm.kv_empty[st]);
@@ -289,6 +293,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
     const int row = qt * kTileQ + r;
     const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
     float m_run = -INFINITY, l_run = 0.f;
+    float o_reg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o_reg[i] = 0.f;
     for (int j = 0; j < nKt; ++j) {
       const int key0 = j * kTileK;
       const bool masked = tile_needs_mask(prm.mask, bh, prm.Lk, key0, lane);   // warp-uniform
@@ -304,14 +311,25 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
       l_run = l_run * alpha + l_tile;
       // rescale the running output (previous PV MMAs are complete: s_full was committed after them).
       // tcgen05.ld/st are warp-collective (.sync.aligned): the branch must be warp-uniform
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+      if (j > 0 && j % kFlushTiles == 0) {
+        // fold the tensor-memory accumulator into the register accumulator; the next PV MMAs restart it
+        float t0[16], t1[16];
+        tmem_ld16(t_row + kTmemO, t0);
+        tmem_ld16(t_row + kTmemO + 16, t1);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {          // both halves of the accumulator: P V_hi and P V_lo
-          float o[16];
-          tmem_ld16(t_row + kTmemO + h * 16, o);
+        for (int i = 0; i < 16; ++i) o_reg[i] = (o_reg[i] + (t0[i] + t1[i])) * alpha;
+      } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] *= alpha;
-          tmem_st16(t_row + kTmemO + h * 16, o);
+        for (int i = 0; i < 16; ++i) o_reg[i] *= alpha;
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {          // both halves of the accumulator: P V_hi and P V_lo
+            float o[16];
+            tmem_ld16(t_row + kTmemO + h * 16, o);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] *= alpha;
+            tmem_st16(t_row + kTmemO + h * 16, o);
+          }
         }
       }
       m_run = m_new;
@@ -325,7 +343,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
     tmem_ld16(t_row + kTmemO, o);
     tmem_ld16(t_row + kTmemO + 16, o2);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] += o2[i];
+    for (int i = 0; i < 16; ++i) o[i] = o_reg[i] + (o[i] + o2[i]);
     if (row < prm.Lq) {
       const float inv = 1.f / l_run;   // fully masked row: 0 * inf = NaN, like softmax over all -inf
       float* dst = prm.out + ((size_t)bh * prm.Lq + row) * prm.dv;
