@@ -223,32 +223,45 @@ def inference_leg(model, dev, peaks, steps, warmup, rank=0, world=1, sampler=Non
     units = it_sum * n_pts * (4 * C_EMB + 4)
     ach = units / max(per_launch_s, 1e-12) / 1e9
     total_img = world * steps
-    # parity flags against the oracle and the real scikit-learn on the last image (outside the timed region)
+    # parity flags against the oracle and the real scikit-learn on ALL benchmark images (outside the timed region)
     from oracle import kmeans as KM
-    sem, emb = model.predict_device(tens[(steps - 1) % 4])
-    fg, X = KM.gather_foreground(sem[0].cpu().numpy(), emb[0].cpu().numpy())
     flags = {}
-    if rank == 0 and len(X) >= N_OBJ:
-        o = KM.kmeans_oracle(X, N_OBJ, seed=0)
-        got = pred.cluster_device(sem[0], emb[0], N_OBJ)[1].cpu().numpy()
-        flags["labels_identical_to_oracle"] = bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"])))
-        sk = KM.sklearn_fit_predict(X, N_OBJ, 0)
-        flags["labels_identical_to_sklearn_up_to_permutation"] = bool(KM.same_up_to_permutation(got[fg != 0], sk + 1))
-        flags["sklearn_partition_agreement"] = KM.partition_agreement(got[fg != 0], sk + 1)
-        if not flags["labels_identical_to_sklearn_up_to_permutation"]:
-            # quantify the mismatch: scikit-learn's own fp32 sums depend on the BLAS kernel / thread count, and its
-            # tol-based stop can end one Lloyd iteration earlier or later on near-tied inputs (random-init embeddings)
-            def inertia(lab):
-                x = X.astype(np.float64)
-                return float(sum(((x[lab == c] - x[lab == c].mean(0)) ** 2).sum() for c in np.unique(lab)))
-            flags["inertia_rel_diff_vs_sklearn"] = (inertia(got[fg != 0]) - inertia(sk + 1)) / inertia(sk + 1)
-            try:
-                from threadpoolctl import threadpool_limits
-                with threadpool_limits(limits=1):
-                    sk1 = KM.sklearn_fit_predict(X, N_OBJ, 0)
-                flags["sklearn_self_agreement_1_vs_all_threads"] = KM.partition_agreement(sk1 + 1, sk + 1)
-            except Exception:
-                pass
+    if rank == 0:
+        ident_o, ident_s, agree, inertia_d, self_agree = [], [], [], [], []
+        for ti in range(len(tens)):
+            sem, emb = model.predict_device(tens[ti])
+            fg, X = KM.gather_foreground(sem[0].cpu().numpy(), emb[0].cpu().numpy())
+            if len(X) < N_OBJ:
+                continue
+            o = KM.kmeans_oracle(X, N_OBJ, seed=0)
+            got = pred.cluster_device(sem[0], emb[0], N_OBJ)[1].cpu().numpy()
+            ident_o.append(bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"]))))
+            sk = KM.sklearn_fit_predict(X, N_OBJ, 0)
+            ident_s.append(bool(KM.same_up_to_permutation(got[fg != 0], sk + 1)))
+            agree.append(round(float(KM.partition_agreement(got[fg != 0], sk + 1)), 5))
+            if not ident_s[-1]:
+                # quantify the mismatch: scikit-learn's own fp32 sums depend on the BLAS kernel / thread count, and its
+                # tol-based stop can end one Lloyd iteration earlier or later on near-tied inputs (random-init embeddings)
+                def inertia(lab):
+                    x = X.astype(np.float64)
+                    return float(sum(((x[lab == c] - x[lab == c].mean(0)) ** 2).sum() for c in np.unique(lab)))
+                inertia_d.append((inertia(got[fg != 0]) - inertia(sk + 1)) / inertia(sk + 1))
+                try:
+                    from threadpoolctl import threadpool_limits
+                    with threadpool_limits(limits=1):
+                        sk1 = KM.sklearn_fit_predict(X, N_OBJ, 0)
+                    self_agree.append(round(float(KM.partition_agreement(sk1 + 1, sk + 1)), 5))
+                except Exception:
+                    pass
+        flags["labels_identical_to_oracle"] = bool(ident_o) and all(ident_o)
+        flags["labels_identical_to_sklearn_up_to_permutation"] = bool(ident_s) and all(ident_s)
+        flags["images_checked"] = len(ident_o)
+        flags["images_identical_to_sklearn"] = int(sum(ident_s))
+        flags["sklearn_partition_agreement"] = min(agree) if agree else None
+        if inertia_d:
+            flags["inertia_rel_diff_vs_sklearn"] = inertia_d
+        if self_agree:
+            flags["sklearn_self_agreement_1_vs_all_threads"] = self_agree
     leg = {
         "value": total_img / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
         "config": {"workload": INFER_WORKLOAD,

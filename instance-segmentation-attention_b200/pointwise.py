@@ -251,6 +251,7 @@ def pixel_heads(xa, xb, head0, head1=None):
     Ca, Cb = xa.shape[1], xb.shape[1]
     Co = head0.out_channels + (head1.out_channels if head1 is not None else 0)
     fused = (xa.dtype == torch.float32 and Ca % 2 == 0 and Cb % 2 == 0 and Co <= 32 and head0.kernel_size == (1, 1)
+             and xa.shape[2] * xa.shape[3] >= 128
              and head0.bias is not None and (head1 is None or (head1.kernel_size == (1, 1) and head1.bias is not None)))
     if not fused:
         y = torch.cat((xa, xb), dim=1)
