@@ -59,6 +59,39 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const SplitParams p) 
   }
 }
 
+// cols / 4 <= 256: thread t < A (A = largest multiple of cols/4 <= 256) owns column group t % (cols/4) for the whole
+// kernel and walks the rows with a fixed stride -- no per-element index division (the generic kernel below pays a 64-bit
+// division per 16 bytes), two rows in flight per thread
+__global__ void __launch_bounds__(256) split_bf16x3_rows_kernel(const SplitParams p) {
+  const int c4 = p.cols >> 2;
+  const int rpi = 256 / c4;
+  const int t = threadIdx.x;
+  if (t >= rpi * c4) return;
+  const int c = (t % c4) << 2;
+  const long long rstep = (long long)gridDim.x * rpi;
+#pragma unroll 2
+  for (long long r = (long long)blockIdx.x * rpi + t / c4; r < p.rows; r += rstep) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = true;
+    if (p.pos_step != 0) {
+      const int pos = (int)((r / p.pos_div) % p.pos_mod) + p.pos_step;
+      ok = pos >= 0 && pos < p.pos_mod;
+    }
+    if (ok) v = __ldg(reinterpret_cast<const float4*>(p.src + (r + p.shift) * p.src_ld + c));
+    __nv_bfloat16 h[4], l[4];
+    split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
+    uint2 hv, lv;
+    hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    __nv_bfloat16* d0 = p.dst + r * p.dst_ld + c;
+    *reinterpret_cast<uint2*>(d0) = hv;
+    *reinterpret_cast<uint2*>(d0 + p.part_stride) = p.order == 0 ? hv : lv;
+    *reinterpret_cast<uint2*>(d0 + 2 * p.part_stride) = p.order == 0 ? lv : hv;
+  }
+}
+
 }  // namespace
 
 extern "C" int isa_split_bf16x3(const float* src, long long rows, int cols, long long src_ld, void* dst, long long dst_ld,
@@ -78,11 +111,18 @@ extern "C" int isa_split_bf16x3(const float* src, long long rows, int cols, long
   p.src = src; p.dst = reinterpret_cast<__nv_bfloat16*>(dst);
   p.rows = rows; p.src_ld = src_ld; p.dst_ld = dst_ld; p.part_stride = part_stride; p.shift = shift;
   p.cols = cols; p.order = order; p.pos_div = pos_div; p.pos_mod = pos_mod; p.pos_step = pos_step;
-  const long long total = rows * (cols / 4);
-  long long blocks = (total + 255) / 256;
   const long long cap = (long long)di.num_sms * 16;
-  if (blocks > cap) blocks = cap;
-  split_bf16x3_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  if (cols / 4 <= 256) {
+    const int rpi = 256 / (cols / 4);
+    long long blocks = (rows + rpi - 1) / rpi;
+    if (blocks > cap) blocks = cap;
+    split_bf16x3_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  } else {
+    const long long total = rows * (cols / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    split_bf16x3_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  }
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }
