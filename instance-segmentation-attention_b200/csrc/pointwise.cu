@@ -10,6 +10,9 @@
 //                 (/root/reference/code/lib/archs/modules/utils.py:218-219), forward and backward with the
 //                 gamma / beta gradients, one row per thread (d_model = 24 floats live in registers).
 #include "isa_common.cuh"
+#include "isa_ptx.cuh"
+#include "isa_tcgen05.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -244,6 +247,13 @@ int launch_ln_bwd(const float* gy, const float* x, const float* res, const float
 bool ln_width_ok(int C) { return C == 8 || C == 16 || C == 24 || C == 32 || C == 40 || C == 48 || C == 64; }
 
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ pixel heads
 // The semantic / embedding heads are 1x1 convolutions over the concatenation [up-sampled features | skip]
 // (/root/reference/code/lib/archs/reseg.py:122-126).  As plain library ops that is a 478 MB concatenation, two cuDNN
@@ -326,6 +336,135 @@ __global__ void __launch_bounds__(kHeadThreads) pixel_heads_fwd_kernel(const Hea
       }
     }
   }
+}
+
+
+// ---- tensor-core pixel heads (Ca + Cb <= 128, Co <= 32): the FFMA kernels above are bound by the delivery of the weight
+// operand from shared memory (a broadcast LDS.128 costs four passes for 16 useful bytes).  Here a 128-pixel tile is a
+// [128 x K] x [K x 32] product on tcgen05: every thread converts ITS pixel's row (staged in shared memory by coalesced
+// loads) to bf16 hi / lo pairs and writes it into tensor memory as the A operand (TMEM lane = pixel); the stacked weights
+// are a K-major bf16 hi / lo B operand built once per CTA; a_hi [b_hi ; b_lo] (N = 64) + a_lo b_hi (N = 32) per k-step
+// keeps fp32-level accuracy (error ~2^-16).  The epilogue reads the pixel's 2 x 32 accumulator columns and stores NCHW.
+constexpr int kHtKP = 128;                       // padded reduction length
+constexpr int kHtSbo = (kHtKP / 8) * 128;        // 2048: byte stride between 8-row groups of a K-major [rows][128] operand
+constexpr int kHtWPart = 4 * kHtSbo;             // 32 rows: 8192 bytes per part (hi | lo contiguous = one N = 64 operand)
+
+__global__ void __launch_bounds__(kHeadThreads) pixel_heads_fwd_tc_kernel(const HeadsParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw_h[];
+  unsigned char* sm = smem_raw_h + ((128u - (smem_u32(smem_raw_h) & 127u)) & 127u);
+  const int K = p.Ca + p.Cb, Co = p.Co0 + p.Co1;
+  const int KS = K;                        // even row stride: 8-byte cp.async destinations (row reads are 2-way conflicted)
+  unsigned char* s_w = sm;                                               // [W_hi ; W_lo] K-major, 2 x 8192 B
+  float* s_x = reinterpret_cast<float*>(sm + 2 * kHtWPart);              // [kHeadTile][KS]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_x + kHeadTile * KS + 1);
+  s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_bar) + 7) & ~uintptr_t(7));
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int pp = threadIdx.x;                                            // pixel inside the tile = TMEM lane
+
+  // weights -> bf16 hi / lo K-major operand (element (n = co, k) at (co/8)*2048 + (k/8)*128 + (co%8)*16 + (k%8)*2)
+  for (int i = threadIdx.x; i < 32 * kHtKP; i += kHeadThreads) {
+    const int co = i / kHtKP, k = i % kHtKP;
+    const float v = (co < Co && k < K) ? __ldg(p.w + (size_t)co * K + k) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int off = (co >> 3) * kHtSbo + (k >> 3) * 128 + (co & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(s_w + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(s_w + kHtWPart + off) = l;
+  }
+  if (threadIdx.x == 0) { mbar_init(s_bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(s_tmem, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);           // 4 warps = the 4 TMEM lane quarters
+  constexpr uint32_t kA_hi = 0, kA_lo = 64, kD = 128;
+  const uint32_t el = elect_one();
+  const uint64_t b_desc = make_desc(smem_u32(s_w), 128, kHtSbo);
+  constexpr uint32_t idesc64 = make_idesc(128, 64), idesc32 = make_idesc(128, 32);
+  float bias[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) bias[c] = (p.bias && c < Co) ? __ldg(p.bias + c) : 0.f;
+
+  const long long n_tiles = (p.P + kHeadTile - 1) / kHeadTile;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kHeadTile;
+    const int np = (int)((p.P - p0) < kHeadTile ? (p.P - p0) : kHeadTile);
+    // ---- stage the tile's rows (contiguous spans of both sources): 8-byte cp.async, everything in flight at once (a
+    //      register-staged loop kept ~4 KB per CTA in flight and made the kernel latency bound: 0.34 ms)
+#pragma unroll 1
+    for (int src = 0; src < 2; ++src) {
+      const float* __restrict__ x = (src == 0 ? p.xa : p.xb);
+      const int Cs = src == 0 ? p.Ca : p.Cb, k0 = src == 0 ? 0 : p.Ca;
+      const int half = Cs >> 1;
+      if (half == 0) continue;
+      const float inv_half = 1.f / (float)half;
+      const float2* __restrict__ x2 = reinterpret_cast<const float2*>(x + p0 * Cs);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < np * half; i += kHeadThreads) {
+        const int r = __float2int_rd(((float)i + 0.5f) * inv_half), k = (i - r * half) * 2;
+        cp_async8(s_x + r * KS + k0 + k, x2 + i);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- this pixel's row -> packed bf16 hi / lo pairs in tensor memory (8 packed columns per 16 k)
+    {
+      const float* __restrict__ xr = s_x + pp * KS;
+      const bool row_ok = pp < np;
+#pragma unroll 1
+      for (int c8 = 0; c8 < kHtKP / 16; ++c8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = c8 * 16 + 2 * e;
+          const float a = (row_ok && k < K) ? xr[k] : 0.f;
+          const float b = (row_ok && k + 1 < K) ? xr[k + 1] : 0.f;
+          split2(a, b, hi[e], lo[e]);
+        }
+        tmem_st8_issue(t_row + kA_hi + c8 * 8, hi);
+        tmem_st8_issue(t_row + kA_lo + c8 * 8, lo);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < kHtKP / 16; ++kk) {
+        const uint32_t ko = (kk * 256) >> 4;
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_hi + kk * 8, b_desc + ko, idesc64, kk > 0 ? 1u : 0u);   // a_hi x [w_hi ; w_lo]
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_lo + kk * 8, b_desc + ko, idesc32, 1u);                  // a_lo x w_hi
+      }
+      umma_commit_e(el, s_bar);
+    }
+    mbar_wait(s_bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    uint32_t d0[32], d1[32];
+    tmem_ld32_issue(t_row + kD, d0);
+    tmem_ld32_issue(t_row + kD + 32, d1);
+    tmem_ld32_wait(d0);
+    tmem_ld32_wait(d1);
+    if (pp < np) {
+      const long long pix = p0 + pp;
+      const long long n = pix / p.HW, hw = pix - n * p.HW;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (c >= Co) break;
+        const float v = __uint_as_float(d0[c]) + __uint_as_float(d1[c]) + bias[c];
+        if (c < p.Co0) p.out0[(n * p.Co0 + c) * p.HW + hw] = v;
+        else p.out1[(n * p.Co1 + (c - p.Co0)) * p.HW + hw] = v;
+      }
+    }
+    tc_fence_before();      // the next tile's tcgen05.st / MMAs follow the __syncthreads after its staging loop
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 struct HeadsBwdParams {
@@ -428,15 +567,18 @@ __global__ void __launch_bounds__(kWgThreads) pixel_heads_wgrad_kernel(const Hea
     const long long p0 = tile * kWgTile;
     const int np = (int)((p.P - p0) < kWgTile ? (p.P - p0) : kWgTile);
     __syncthreads();
-    // x tile: both sources are contiguous [pixels][Cs] spans
+    // x tile: both sources are contiguous [pixels][Cs] spans, copied with 8-byte cp.async (all in flight at once)
     for (int src = 0; src < 2; ++src) {
       const float* __restrict__ x = src == 0 ? xa : xb;
       const int Cs = src == 0 ? p.Ca : p.Cb, k0 = src == 0 ? 0 : p.Ca;
       const int half = Cs >> 1;
+      if (half == 0) continue;
+      const float inv_half = 1.f / (float)half;
+      const float2* __restrict__ x2 = reinterpret_cast<const float2*>(x + p0 * Cs);
       for (int i = tid; i < kWgTile * half; i += kWgThreads) {
-        const int pp = i / half, k = (i - pp * half) * 2;
-        const float2 v = pp < np ? *reinterpret_cast<const float2*>(x + (p0 + pp) * Cs + k) : make_float2(0.f, 0.f);
-        *reinterpret_cast<float2*>(s_x + pp * Kp + k0 + k) = v;
+        const int pp = __float2int_rd(((float)i + 0.5f) * inv_half), k = (i - pp * half) * 2;
+        if (pp < np) cp_async8(s_x + pp * Kp + k0 + k, x2 + i);
+        else *reinterpret_cast<float2*>(s_x + pp * Kp + k0 + k) = make_float2(0.f, 0.f);
       }
     }
     // g tile, transposed: lanes run along the pixels (coalesced plane reads)
@@ -451,6 +593,7 @@ __global__ void __launch_bounds__(kWgThreads) pixel_heads_wgrad_kernel(const Hea
       }
       s_g[pp * COP + c] = v;
     }
+    cp_async_wait_all();
     __syncthreads();
     if (worker) {
 #pragma unroll 4
@@ -618,6 +761,16 @@ int isa_pixel_heads_fwd(const float* xa, int Ca, const float* xb, int Cb, const 
   const int Co = Co0 + Co1, cop = (Co + 3) & ~3;
   const long long n_tiles = (P + kHeadTile - 1) / kHeadTile;
   long long grid = n_tiles < (long long)di.num_sms * 3 ? n_tiles : (long long)di.num_sms * 3;
+  if (Ca + Cb <= kHtKP && !getenv("ISA_HEADS_FFMA")) {
+    // tensor-core path: 2 CTAs per SM (256 TMEM columns each)
+    size_t smem = 2 * kHtWPart + (size_t)kHeadTile * (Ca + Cb) * sizeof(float) + 64 + 128;
+    if (smem < 80 * 1024) smem = 80 * 1024;     // never three CTAs on one SM: the third would spin in tcgen05.alloc
+    grid = n_tiles < (long long)di.num_sms * 2 ? n_tiles : (long long)di.num_sms * 2;
+    ISA_CUDA(cudaFuncSetAttribute(pixel_heads_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pixel_heads_fwd_tc_kernel<<<(unsigned)grid, kHeadThreads, smem, stream>>>(hp);
+    ISA_CUDA(cudaGetLastError());
+    return ISA_OK;
+  }
 #define ISA_HEADS_FWD(COP)                                                                                              \
   {                                                                                                                     \
     const size_t smem = ((size_t)(Ca + Cb) * COP + (size_t)kHeadTile * ((Ca + Cb) | 1)) * sizeof(float);                \
