@@ -537,6 +537,122 @@ __global__ void __launch_bounds__(kHeadThreads) pixel_heads_bwd_kernel(const Hea
   }
 }
 
+
+// ---- tensor-core source gradient of the heads: [128 pixels x 32] x [32 x K]: the pixel's output gradient (read from the
+// NCHW planes: coalesced) is the A operand in tensor memory, the stacked weights a K-major [N = k][K = co] B operand;
+// the accumulator row (K columns) goes through shared memory to the NHWC rows with coalesced 8-byte stores.
+constexpr int kHbSbo = (32 / 8) * 128;           // 512: byte stride between 8-row groups of the [128 k][32 co] operand
+constexpr int kHbWPart = 16 * kHbSbo;            // 8192 bytes per part
+
+__global__ void __launch_bounds__(kHeadThreads) pixel_heads_bwd_tc_kernel(const HeadsBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw_h[];
+  unsigned char* sm = smem_raw_h + ((128u - (smem_u32(smem_raw_h) & 127u)) & 127u);
+  const int K = p.Ca + p.Cb, Co = p.Co0 + p.Co1;
+  const int KS = K;
+  unsigned char* s_w = sm;                                               // W_hi | W_lo, [128 k][32 co] K-major
+  float* s_o = reinterpret_cast<float*>(sm + 2 * kHbWPart);              // [kHeadTile][KS]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_o + kHeadTile * KS) + 7) & ~uintptr_t(7));
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int pp = threadIdx.x;
+
+  for (int i = threadIdx.x; i < kHtKP * 32; i += kHeadThreads) {
+    const int k = i >> 5, co = i & 31;
+    const float v = (co < Co && k < K) ? __ldg(p.w + (size_t)co * K + k) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int off = (k >> 3) * kHbSbo + (co >> 3) * 128 + (k & 7) * 16 + (co & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(s_w + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(s_w + kHbWPart + off) = l;
+  }
+  if (threadIdx.x == 0) { mbar_init(s_bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(s_tmem, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t kA_hi = 0, kA_lo = 16, kD = 32;
+  const uint32_t el = elect_one();
+  const uint64_t b_hi = make_desc(smem_u32(s_w), 128, kHbSbo), b_lo = make_desc(smem_u32(s_w + kHbWPart), 128, kHbSbo);
+  constexpr uint32_t idesc = make_idesc(128, kHtKP);
+
+  const long long n_tiles = (p.P + kHeadTile - 1) / kHeadTile;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kHeadTile;
+    const int np = (int)((p.P - p0) < kHeadTile ? (p.P - p0) : kHeadTile);
+    // ---- this pixel's output gradient -> packed bf16 hi / lo pairs in tensor memory
+    {
+      const long long pix = p0 + pp;
+      const long long n = pix / p.HW, hw = pix - n * p.HW;
+      float g[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float v = 0.f;
+        if (pp < np && c < Co) {
+          if (c < p.Co0) { if (p.g0) v = __ldg(p.g0 + (n * p.Co0 + c) * p.HW + hw); }
+          else if (p.g1) v = __ldg(p.g1 + (n * p.Co1 + (c - p.Co0)) * p.HW + hw);
+        }
+        g[c] = v;
+      }
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) split2(g[2 * e], g[2 * e + 1], hi[e], lo[e]);
+      tmem_st16_issue(t_row + kA_hi, hi);
+      tmem_st16_issue(t_row + kA_lo, lo);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();           // also: the previous tile's copy-out of s_o is complete
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t ko = (kk * 256) >> 4;
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_hi + kk * 8, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_hi + kk * 8, b_lo + ko, idesc, 1u);
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_lo + kk * 8, b_hi + ko, idesc, 1u);
+      }
+      umma_commit_e(el, s_bar);
+    }
+    mbar_wait(s_bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    {
+      float* __restrict__ orow = s_o + pp * KS;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t d[32];
+        tmem_ld32_issue(t_row + kD + c * 32, d);
+        tmem_ld32_wait(d);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < K) orow[c * 32 + i] = __uint_as_float(d[i]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+#pragma unroll 1
+    for (int src = 0; src < 2; ++src) {
+      float* __restrict__ gx = src == 0 ? p.ga : p.gb;
+      const int Cs = src == 0 ? p.Ca : p.Cb, k0 = src == 0 ? 0 : p.Ca;
+      if (Cs == 0 || gx == nullptr) continue;
+      const int half = Cs >> 1;
+      const float inv_half = 1.f / (float)half;
+      float2* __restrict__ o2 = reinterpret_cast<float2*>(gx + p0 * Cs);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < np * half; i += kHeadThreads) {
+        const int r = __float2int_rd(((float)i + 0.5f) * inv_half), k = (i - r * half) * 2;
+        o2[i] = *reinterpret_cast<const float2*>(s_o + r * KS + k0 + k);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // Weight / bias gradient of the stacked heads: dW[co][k] = sum_p g[co][p] x[p][k], db[co] = sum_p g[co][p].
 // Each CTA reduces a strided set of 64-pixel tiles staged in shared memory (g transposed to [p][co], x as [p][k]); a thread
 // owns a 4 (co) x 4 (k) register tile: per pixel one broadcast LDS.128 of g and one LDS.128 of x feed 16 FMAs.  Partials
@@ -804,6 +920,15 @@ int isa_pixel_heads_bwd(const float* g0, int Co0, const float* g1, int Co1, cons
   const long long n_tiles = (P + kHeadTile - 1) / kHeadTile;
   long long grid = n_tiles < (long long)di.num_sms * 3 ? n_tiles : (long long)di.num_sms * 3;
   const int Kp = (Ca + Cb + 3) & ~3;
+  if (Ca + Cb <= kHtKP && !getenv("ISA_HEADS_FFMA")) {
+    size_t smem = 2 * kHbWPart + (size_t)kHeadTile * (Ca + Cb) * sizeof(float) + 64 + 128;
+    if (smem < 80 * 1024) smem = 80 * 1024;     // at most two CTAs per SM (256 TMEM columns each)
+    grid = n_tiles < (long long)di.num_sms * 2 ? n_tiles : (long long)di.num_sms * 2;
+    ISA_CUDA(cudaFuncSetAttribute(pixel_heads_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pixel_heads_bwd_tc_kernel<<<(unsigned)grid, kHeadThreads, smem, stream>>>(hp);
+    ISA_CUDA(cudaGetLastError());
+    return ISA_OK;
+  }
 #define ISA_HEADS_BWD(COP)                                                                                              \
   {                                                                                                                     \
     const size_t smem = ((size_t)Kp * COP + (size_t)kHeadTile * (Kp | 1)) * sizeof(float);                              \
