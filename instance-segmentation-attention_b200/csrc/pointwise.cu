@@ -742,6 +742,141 @@ __global__ void __launch_bounds__(kWgThreads) pixel_heads_wgrad_kernel(const Hea
   }
 }
 
+// ---- tensor-core weight / bias gradient of the heads: D[k][co] += sum_pixels x[pixel][k] g[pixel][co], accumulated in
+// tensor memory over ALL tiles of the (persistent) CTA.  A = x^T: TMEM lane = source channel k, a tile's 128 pixels are
+// the reduction dimension (thread k reads column k of the staged tile: conflict free); row K of A is all ones, so row K
+// of D is the bias gradient.  B = g^T [N = co][K = pixels], bf16 hi / lo K-major in shared memory, rebuilt per tile by
+// the thread that owns the pixel.  Per-CTA partials go to the workspace, summed in fixed order by column_reduce_kernel.
+__global__ void __launch_bounds__(kHeadThreads) pixel_heads_wgrad_tc_kernel(const HeadsBwdParams p, const float* __restrict__ xa,
+                                                                          const float* __restrict__ xb, float* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw_h[];
+  unsigned char* sm = smem_raw_h + ((128u - (smem_u32(smem_raw_h) & 127u)) & 127u);
+  const int K = p.Ca + p.Cb, Co = p.Co0 + p.Co1;
+  const int KS = K;
+  unsigned char* s_g = sm;                                               // [G_hi ; G_lo], [32 co][128 pixels] K-major
+  float* s_x = reinterpret_cast<float*>(sm + 2 * kHtWPart);              // [kHeadTile][KS]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_x + kHeadTile * KS) + 7) & ~uintptr_t(7));
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int t = threadIdx.x;                      // pixel of the tile when building B, source channel k when building A
+
+  for (int i = threadIdx.x; i < (2 * kHtWPart) / 4; i += kHeadThreads) reinterpret_cast<uint32_t*>(s_g)[i] = 0u;
+  if (threadIdx.x == 0) { mbar_init(s_bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(s_tmem, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t kA_hi = 0, kA_lo = 64, kD = 128;
+  const uint32_t el = elect_one();
+  const uint64_t b_desc = make_desc(smem_u32(s_g), 128, kHtSbo);
+  constexpr uint32_t idesc64 = make_idesc(128, 64), idesc32 = make_idesc(128, 32);
+  const int b_off = (t >> 3) * 128 + (t & 7) * 2;          // this pixel's slot inside each 8-row group of the B operand
+
+  const long long n_tiles = (p.P + kHeadTile - 1) / kHeadTile;
+  int done = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++done) {
+    const long long p0 = tile * kHeadTile;
+    const int np = (int)((p.P - p0) < kHeadTile ? (p.P - p0) : kHeadTile);
+    // ---- x tile -> shared memory (the previous tile's readers finished before its MMAs were issued)
+#pragma unroll 1
+    for (int src = 0; src < 2; ++src) {
+      const float* __restrict__ x = src == 0 ? xa : xb;
+      const int Cs = src == 0 ? p.Ca : p.Cb, k0 = src == 0 ? 0 : p.Ca;
+      const int half = Cs >> 1;
+      if (half == 0) continue;
+      const float inv_half = 1.f / (float)half;
+      const float2* __restrict__ x2 = reinterpret_cast<const float2*>(x + p0 * Cs);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < np * half; i += kHeadThreads) {
+        const int r = __float2int_rd(((float)i + 0.5f) * inv_half), k = (i - r * half) * 2;
+        cp_async8(s_x + r * KS + k0 + k, x2 + i);
+      }
+    }
+    // ---- this pixel's output gradient (NCHW planes: coalesced)
+    float g[32];
+    {
+      const long long pix = p0 + t;
+      const long long n = pix / p.HW, hw = pix - n * p.HW;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float v = 0.f;
+        if (t < np && c < Co) {
+          if (c < p.Co0) { if (p.g0) v = __ldg(p.g0 + (n * p.Co0 + c) * p.HW + hw); }
+          else if (p.g1) v = __ldg(p.g1 + (n * p.Co1 + (c - p.Co0)) * p.HW + hw);
+        }
+        g[c] = v;
+      }
+    }
+    // the previous tile's MMAs must be done with the B operand and the A columns before either is rewritten
+    if (done > 0) { mbar_wait(s_bar, (done - 1) & 1); tc_fence_after(); }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(g[c]);
+      const __nv_bfloat16 l = __float2bfloat16_rn(g[c] - __bfloat162float(h));
+      const int off = (c >> 3) * kHtSbo + (c & 7) * 16 + b_off;
+      *reinterpret_cast<__nv_bfloat16*>(s_g + off) = h;
+      *reinterpret_cast<__nv_bfloat16*>(s_g + kHtWPart + off) = l;
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
+    __syncthreads();
+    // ---- column t of the tile (source channel t over the 128 pixels) -> packed bf16 hi / lo pairs in tensor memory
+    {
+      const int k = t;
+#pragma unroll 1
+      for (int c8 = 0; c8 < kHeadTile / 16; ++c8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int r0 = c8 * 16 + 2 * e;
+          float a = 0.f, b = 0.f;
+          if (k < K) { a = r0 < np ? s_x[r0 * KS + k] : 0.f; b = r0 + 1 < np ? s_x[(r0 + 1) * KS + k] : 0.f; }
+          else if (k == K) { a = r0 < np ? 1.f : 0.f; b = r0 + 1 < np ? 1.f : 0.f; }     // ones row: bias gradient
+          split2(a, b, hi[e], lo[e]);
+        }
+        tmem_st8_issue(t_row + kA_hi + c8 * 8, hi);
+        tmem_st8_issue(t_row + kA_lo + c8 * 8, lo);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < kHeadTile / 16; ++kk) {
+        const uint32_t ko = (kk * 256) >> 4;
+        const uint32_t acc = (done > 0 || kk > 0) ? 1u : 0u;
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_hi + kk * 8, b_desc + ko, idesc64, acc);       // x_hi x [g_hi ; g_lo]
+        umma_bf16_ts_e(el, tmem + kD, tmem + kA_lo + kk * 8, b_desc + ko, idesc32, 1u);        // x_lo x g_hi
+      }
+      umma_commit_e(el, s_bar);
+    }
+  }
+  if (done > 0) { mbar_wait(s_bar, (done - 1) & 1); tc_fence_after(); }
+  uint32_t d0[32], d1[32];
+  tmem_ld32_issue(t_row + kD, d0);
+  tmem_ld32_issue(t_row + kD + 32, d1);
+  tmem_ld32_wait(d0);
+  tmem_ld32_wait(d1);
+  if (t <= K) {
+    float* row = partial + (size_t)blockIdx.x * (Co * K + Co);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c >= Co) break;
+      const float v = done > 0 ? __uint_as_float(d0[c]) + __uint_as_float(d1[c]) : 0.f;
+      if (t < K) row[c * K + t] = v;
+      else row[Co * K + c] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 int heads_check(int Ca, int Cb, int Co0, int Co1, long long P, int HW) {
   ISA_CHECK_ARG(Ca > 0 && Cb >= 0 && Ca % 2 == 0 && Cb % 2 == 0, "pixel_heads: source widths must be even (Ca=%d Cb=%d)", Ca, Cb);
   ISA_CHECK_ARG(Co0 > 0 && Co1 >= 0 && Co0 + Co1 <= 32, "pixel_heads: at most 32 stacked output channels (Co0=%d Co1=%d)", Co0, Co1);
@@ -974,6 +1109,19 @@ int isa_pixel_heads_wgrad(const float* g0, int Co0, const float* g1, int Co1, co
   const long long n_tiles = (P + kWgTile - 1) / kWgTile;
   const int grid = (int)(n_tiles < (long long)di.num_sms * 2 ? n_tiles : (long long)di.num_sms * 2);
   float* partial = reinterpret_cast<float*>(workspace);
+  if (K + 1 <= kHtKP && !getenv("ISA_HEADS_FFMA")) {
+    size_t smem = 2 * kHtWPart + (size_t)kHeadTile * K * sizeof(float) + 64 + 128;
+    if (smem < 80 * 1024) smem = 80 * 1024;     // at most two CTAs per SM (256 TMEM columns each)
+    const long long nt = (P + kHeadTile - 1) / kHeadTile;
+    const int g2 = (int)(nt < (long long)di.num_sms * 2 ? nt : (long long)di.num_sms * 2);
+    ISA_CUDA(cudaFuncSetAttribute(pixel_heads_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pixel_heads_wgrad_tc_kernel<<<g2, kHeadThreads, smem, stream>>>(hp, xa, xb, partial);
+    ISA_CUDA(cudaGetLastError());
+    const int R2 = Co * K + Co;
+    column_reduce_kernel<<<(R2 + 31) / 32, 256, 0, stream>>>(partial, g2, R2, dw_db);
+    ISA_CUDA(cudaGetLastError());
+    return ISA_OK;
+  }
 #define ISA_HEADS_WG(COP)                                                                                                  \
   {                                                                                                                        \
     const size_t smem = (size_t)kWgTile * (KG * 4 + COP) * sizeof(float);                                                  \
