@@ -47,5 +47,5 @@ def build_model_and_prediction(dataset, model_path, seed=0):
                   load_model_path=model_path or '', usegpu=True, n_embedding=ms.D_MODEL,
                   n_objects_prediction=ms.N_OBJECTS_PREDICTION,
                   net_kwargs=dict(n_units=ms.N_RENET_UNITS, n_head=ms.N_HEAD, d_k=ms.D_K, d_v=ms.D_V))
-    prediction = Prediction(ms.IMAGE_HEIGHT, ms.IMAGE_WIDTH, ms.MEAN, ms.STD, False, model, 1, seed=seed)
+    prediction = Prediction(ms.IMAGE_HEIGHT, ms.IMAGE_WIDTH, ms.MEAN, ms.STD, False, model, 1, seed=seed, strict=False)
     return model, prediction

@@ -291,6 +291,14 @@ size_t isa_pixel_heads_wgrad_workspace_bytes(int Ca, int Cb, int Co0, int Co1);
 int isa_pixel_heads_wgrad(const float* g0, int Co0, const float* g1, int Co1, const float* xa, int Ca, const float* xb, int Cb,
                           long long P, int HW, float* dw_db, void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
+/* ------------------------------------------------------------------ 2x2 / stride-2 max pool (NHWC)
+ * The nn.MaxPool2d(2, 2) between the backbone's convolution stages (/root/reference/code/lib/archs/modules/vgg16.py:82-140)
+ * on channels-last activations: x [N][H][W][C] -> y [N][H/2][W/2][C] (floor mode, C % 4 == 0); idx (u8, shape of y, NULL at
+ * inference) records the window position 0..3 of the maximum (first maximum in row-major order, NaN wins, like PyTorch);
+ * the backward scatters gy through idx into gx [N][H][W][C]. */
+int isa_maxpool2x2_fwd(const float* x, int N, int H, int W, int C, float* y, unsigned char* idx, isa_stream_t stream);
+int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, float* gx, isa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

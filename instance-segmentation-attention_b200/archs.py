@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .attention import MultiHeadAttention
-from .pointwise import ConvBiasAct, ConvTransposeBiasAct, pixel_heads, thin_linear
+from .pointwise import ConvBiasAct, ConvTransposeBiasAct, MaxPool2x2, pixel_heads, thin_linear
 from .renet import ReNet
 
 
@@ -40,7 +40,7 @@ class SkipVGG16(nn.Module):
         self.stage1 = block(n_input, 64, 2)
         self.stage2 = block(64, 128, 2)
         self.stage3 = block(128, 256, 3)
-        self.pool = nn.MaxPool2d(2, 2)
+        self.pool = MaxPool2x2()
 
     def forward(self, x):
         s1 = self.stage1(x)

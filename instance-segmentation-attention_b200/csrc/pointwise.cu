@@ -247,6 +247,61 @@ int launch_ln_bwd(const float* gy, const float* x, const float* res, const float
 bool ln_width_ok(int C) { return C == 8 || C == 16 || C == 24 || C == 32 || C == 40 || C == 48 || C == 64; }
 
 
+
+// ------------------------------------------------------------------------------------------------ 2x2 / stride-2 max pool
+// The backbone's nn.MaxPool2d(2, 2) on NHWC activations (/root/reference/code/lib/archs/modules/vgg16.py:82-140 pools
+// between the conv stages).  Forward keeps the window position of the maximum (first maximum in row-major window order,
+// NaN wins, like PyTorch) as one byte per output element, so the backward is a pure scatter: read gy + index, write
+// the four window positions (PyTorch's NHWC backward re-reads the indices as int64 and measured 2.4x the forward).
+__global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ idx,
+                                                             long long total4, int Ho, int Wo, int W, int C4, long long in_img) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long r = i / C4;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long n = r / Ho;
+    const long long base = n * in_img + ((long long)(2 * ho) * W + 2 * wo) * (C4 * 4) + c4 * 4;
+    const float4 a = ld4(x + base), b = ld4(x + base + C4 * 4);
+    const float4 c = ld4(x + base + (long long)W * C4 * 4), d = ld4(x + base + (long long)W * C4 * 4 + C4 * 4);
+    float4 m; unsigned int sel = 0;
+#define ISA_POOL1(F, SH)                                                         \
+    {                                                                            \
+      float best = a.F; unsigned int bi = 0;                                     \
+      if (b.F > best || b.F != b.F) { best = b.F; bi = 1; }                      \
+      if (c.F > best || c.F != c.F) { best = c.F; bi = 2; }                      \
+      if (d.F > best || d.F != d.F) { best = d.F; bi = 3; }                      \
+      m.F = best; sel |= bi << SH;                                               \
+    }
+    ISA_POOL1(x, 0) ISA_POOL1(y, 8) ISA_POOL1(z, 16) ISA_POOL1(w, 24)
+#undef ISA_POOL1
+    *reinterpret_cast<float4*>(y + i * 4) = m;
+    if (idx) *reinterpret_cast<unsigned int*>(idx + i * 4) = sel;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __restrict__ gy, const unsigned char* __restrict__ idx,
+                                                             float* __restrict__ gx, long long total4, int Ho, int Wo, int W, int C4,
+                                                             long long in_img) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long r = i / C4;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long n = r / Ho;
+    const long long base = n * in_img + ((long long)(2 * ho) * W + 2 * wo) * (C4 * 4) + c4 * 4;
+    const float4 g = ld4(gy + i * 4);
+    const unsigned int sel = *reinterpret_cast<const unsigned int*>(idx + i * 4);
+    const unsigned int s0 = sel & 3u, s1 = (sel >> 8) & 3u, s2 = (sel >> 16) & 3u, s3 = (sel >> 24) & 3u;
+#pragma unroll
+    for (unsigned int q = 0; q < 4; ++q) {
+      float4 o;
+      o.x = s0 == q ? g.x : 0.f; o.y = s1 == q ? g.y : 0.f; o.z = s2 == q ? g.z : 0.f; o.w = s3 == q ? g.w : 0.f;
+      *reinterpret_cast<float4*>(gx + base + (long long)(q >> 1) * W * C4 * 4 + (q & 1) * C4 * 4) = o;
+    }
+  }
+}
+
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -1138,6 +1193,39 @@ int isa_pixel_heads_wgrad(const float* g0, int Co0, const float* g1, int Co1, co
   ISA_CUDA(cudaGetLastError());
   const int R = Co * K + Co;
   column_reduce_kernel<<<(R + 31) / 32, 256, 0, stream>>>(partial, grid, R, dw_db);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+// y [N][H/2][W/2][C] = 2x2 / stride-2 max pool of the NHWC tensor x [N][H][W][C] (floor mode; C % 4 == 0);
+// idx (u8, same shape as y, may be NULL at inference) = window position 0..3 of the maximum.
+int isa_maxpool2x2_fwd(const float* x, int N, int H, int W, int C, float* y, unsigned char* idx, cudaStream_t stream) {
+  ISA_CHECK_ARG(x && y && N > 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0, "maxpool2x2_fwd: bad argument (N=%d H=%d W=%d C=%d)", N, H, W, C);
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const long long total4 = (long long)N * Ho * Wo * C4;
+  long long grid = (total4 + 255) / 256;
+  if (grid > (long long)di.num_sms * 16) grid = (long long)di.num_sms * 16;
+  maxpool2x2_fwd_kernel<<<(unsigned)grid, 256, 0, stream>>>(x, y, idx, total4, Ho, Wo, W, C4, (long long)H * W * C);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+// gx [N][H][W][C] = scatter of gy [N][H/2][W/2][C] to the recorded window positions (every covered element is written;
+// with odd H or W the uncovered last row / column is zeroed first).
+int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, float* gx, cudaStream_t stream) {
+  ISA_CHECK_ARG(gy && idx && gx && N > 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0, "maxpool2x2_bwd: bad argument (N=%d H=%d W=%d C=%d)", N, H, W, C);
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  if ((H & 1) || (W & 1)) ISA_CUDA(cudaMemsetAsync(gx, 0, (size_t)N * H * W * C * sizeof(float), stream));
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const long long total4 = (long long)N * Ho * Wo * C4;
+  long long grid = (total4 + 255) / 256;
+  if (grid > (long long)di.num_sms * 16) grid = (long long)di.num_sms * 16;
+  maxpool2x2_bwd_kernel<<<(unsigned)grid, 256, 0, stream>>>(gy, idx, gx, total4, Ho, Wo, W, C4, (long long)H * W * C);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }

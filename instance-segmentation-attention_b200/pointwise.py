@@ -259,3 +259,42 @@ def pixel_heads(xa, xb, head0, head1=None):
     out0, out1 = _PixelHeadsFn.apply(_nhwc(xa), _nhwc(xb), head0.weight, head0.bias,
                                      head1.weight if head1 is not None else None, head1.bias if head1 is not None else None)
     return out0, (out1 if head1 is not None else None)
+
+
+class _MaxPool2x2Fn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        N, C, H, W = x.shape
+        y = torch.empty(N, C, H // 2, W // 2, device=x.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+        need = ctx.needs_input_grad[0]
+        idx = torch.empty(N, H // 2, W // 2, C, device=x.device, dtype=torch.uint8) if need else None
+        rc = lib.isa_maxpool2x2_fwd(x.data_ptr(), N, H, W, C, y.data_ptr(), _lib.ptr(idx), _lib.stream_ptr(x.device))
+        _lib.check(rc, "isa_maxpool2x2_fwd")
+        ctx.geom = (N, C, H, W)
+        if need:
+            ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        N, C, H, W = ctx.geom
+        idx, = ctx.saved_tensors
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty(N, C, H, W, device=gy.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+        rc = lib.isa_maxpool2x2_bwd(gy.data_ptr(), idx.data_ptr(), N, H, W, C, gx.data_ptr(), _lib.stream_ptr(gy.device))
+        _lib.check(rc, "isa_maxpool2x2_bwd")
+        return gx
+
+
+class MaxPool2x2(nn.Module):
+    """nn.MaxPool2d(2, 2) for NHWC-dense fp32 CUDA activations (index-byte forward, scatter backward); other inputs go to
+    the library op."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            return _MaxPool2x2Fn.apply(x)
+        return F.max_pool2d(x, 2, 2)

@@ -13,6 +13,8 @@ Input images: RGB -> bilinear resize -> ToTensor -> Normalize(mean, std) (3 chan
 21-channel colour-space expansion needs scikit-image, which is not installed, and is data
 preparation, not hot path).
 """
+import sys
+
 import numpy as np
 import torch
 from PIL import Image
@@ -23,7 +25,7 @@ from . import clustering
 class Prediction(object):
 
     def __init__(self, resize_height, resize_width, mean, std, use_coordinates, model, n_workers, seed=0,
-                 n_init=35, max_iter=500):
+                 n_init=35, max_iter=500, strict=True):
         if use_coordinates:
             raise NotImplementedError("use_coordinates=True is off in every shipped setting and not implemented")
         self.mean = np.asarray(mean, dtype=np.float32).reshape(3, 1, 1)
@@ -36,6 +38,10 @@ class Prediction(object):
         self.seed = seed
         self.n_init = n_init
         self.max_iter = max_iter
+        # strict=True raises like scikit-learn / the reference when an image cannot be clustered (fewer foreground
+        # pixels than clusters, non-finite embeddings); strict=False (the list-processing scripts) writes an
+        # all-background instance mask for that image and goes on
+        self.strict = strict
 
     # ---- image loading (prediction.py:32-45)
     def image_to_tensor(self, img):
@@ -77,7 +83,14 @@ class Prediction(object):
         n = self.model.n_objects_prediction
         _, _, ins_up, cls_up, res = self.cluster_device(sem[0], emb[0], n, image_height, image_width)
         both = torch.stack([cls_up, ins_up]).cpu()     # the only D2H copy (also the sync point)
-        res.check()
+        if self.strict:
+            res.check()
+        else:
+            try:
+                res.check()
+            except ValueError as e:
+                sys.stderr.write("warning: image not clustered (%s); writing an empty instance mask\n" % e)
+                return both[0].numpy(), np.zeros_like(both[1].numpy()), 0
         return both[0].numpy(), both[1].numpy(), n
 
     def predict_many(self, raw_images, prefetch=2):
@@ -126,11 +139,15 @@ class Prediction(object):
             if pending is not None:
                 host_p, info_p, ev_p = pending
                 ev_p.synchronize()
-                if int(info_p[0]) == 1:
-                    raise ValueError("n_samples=%d should be >= n_clusters." % int(info_p[2]))
-                if int(info_p[0]) == 2:
-                    raise ValueError("Input X contains NaN or infinity.")
-                yield host_p[0].numpy().copy(), host_p[1].numpy().copy(), n
+                if int(info_p[0]) != 0:
+                    msg = ("n_samples=%d should be >= n_clusters." % int(info_p[2]) if int(info_p[0]) == 1
+                           else "Input X contains NaN or infinity.")
+                    if self.strict:
+                        raise ValueError(msg)
+                    sys.stderr.write("warning: image not clustered (%s); writing an empty instance mask\n" % msg)
+                    yield host_p[0].numpy().copy(), np.zeros_like(host_p[1].numpy()), 0
+                else:
+                    yield host_p[0].numpy().copy(), host_p[1].numpy().copy(), n
             if cur is None:
                 break
             pending = cur

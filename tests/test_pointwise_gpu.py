@@ -124,3 +124,23 @@ def test_pixel_heads_match_conv_of_concatenation(cuda, n, Ca, Cb, H, W, Co0, Co1
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-3)
     finally:
         torch.backends.cudnn.allow_tf32 = True
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 64, 32, 48), (1, 128, 17, 9), (3, 8, 7, 7), (16, 64, 64, 64)])
+def test_maxpool2x2_matches_torch(cuda, N, C, H, W):
+    from isa_b200.pointwise import MaxPool2x2
+    torch.manual_seed(N + C + H)
+    x = torch.randn(N, C, H, W, device=cuda)
+    x = torch.relu(x)                                   # post-ReLU inputs: many exact ties at zero
+    x[0, 0, 0, 0] = float("nan")
+    x = x.contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = MaxPool2x2()(xa)
+    yb = F.max_pool2d(xb, 2, 2)
+    assert torch.equal(torch.nan_to_num(ya, nan=-7.0), torch.nan_to_num(yb, nan=-7.0))
+    g = torch.randn_like(yb)
+    ga, = torch.autograd.grad(ya, xa, g)
+    gb, = torch.autograd.grad(yb, xb, g)
+    assert torch.equal(ga, gb)
+    with torch.no_grad():
+        assert torch.equal(torch.nan_to_num(MaxPool2x2()(x), nan=-7.0), torch.nan_to_num(yb, nan=-7.0))
