@@ -358,16 +358,22 @@ def run_ours(args):
             m = model.train_step(b[0], b[1], b[2], b[3], clip)
             last["loss"] = float(m['Cost'])          # device -> host read of the step's result
 
-        # value: inputs resident in HBM
+        # (a) per-kernel times: an EAGER pass with CUDA events around every C-ABI call (explains the step, is not the value)
         _lib.TIMER.reset()
-        sampler.start()
         timed(step_dev, 0, args.warmup)              # warm-up outside the kernel timers
         _lib.TIMER.enabled = True
-        ms = timed(step_dev, args.steps, 0)
+        ms_eager = timed(step_dev, args.steps, 0)
         _lib.TIMER.enabled = False
-        clocks = sampler.stop()
         summ = _lib.TIMER.summary()
         launches = sum(_lib.KERNELS_PER_CALL[k] * c for k, (c, _) in summ.items())
+        # (b) value: inputs resident in HBM, the step replayed from its CUDA graph (Model.enable_cuda_graph: the same
+        #     ~800 launches per step, submitted by one cudaGraphLaunch instead of one by one from Python)
+        use_graph = not args.no_graph and (world == 1 or os.environ.get("ISA_GRAPH_DDP") == "1")
+        if use_graph:
+            model.enable_cuda_graph(warmup_steps=1)
+        sampler.start()
+        ms = timed(step_dev, args.steps, 3)          # the first warm-up step here captures the graph
+        clocks = sampler.stop()
         ms_e2e = timed(step_e2e, args.steps, 1)
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         total_img = bs * world * args.steps
@@ -389,7 +395,8 @@ def run_ours(args):
             "config": {"workload": TRAIN_WORKLOAD,
                        "per_gpu_batch": bs, "global_batch": bs * world, "parallelism": "dp%d" % world,
                        "l2": "working set (activations) >> 126 MB L2, two alternating input batches",
-                       "target_format_value": "int64 one-hot (reference collate)", "kernel_ms_per_step": kernel_ms},
+                       "target_format_value": "int64 one-hot (reference collate)", "kernel_ms_per_step": kernel_ms,
+                       "cuda_graph": bool(use_graph), "ms_per_step_eager_with_kernel_timers": ms_eager / args.steps},
             "clocks": clocks,
             "e2e": {"value": total_img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
@@ -544,6 +551,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="keep the training step eager (no CUDA-graph replay)")
     ap.add_argument("--no-inference", dest="no_inference", action="store_true",
                     help="train workload: skip the extra pred.py inference leg reported under \"inference\" at N = 1")
     args = ap.parse_args()

@@ -299,6 +299,15 @@ int isa_pixel_heads_wgrad(const float* g0, int Co0, const float* g1, int Co1, co
 int isa_maxpool2x2_fwd(const float* x, int N, int H, int W, int C, float* y, unsigned char* idx, isa_stream_t stream);
 int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, float* gx, isa_stream_t stream);
 
+/* ------------------------------------------------------------------ fused gradient clipping + Adadelta
+ * The tail of the reference's training step (/root/reference/code/lib/model.py:271-281: clip_grad_norm_ then
+ * optimizer.step(); settings/CVPPP/training_settings.py: OPTIMIZER 'Adadelta', LEARNING_RATE 1, WEIGHT_DECAY 1e-3,
+ * CLIP_GRAD_NORM 10) over flat fp32 buffers.  PyTorch's Adadelta arithmetic:
+ *   g += wd p;  v = rho v + (1-rho) g^2;  d = sqrt(u + eps) / sqrt(v + eps) g;  u = rho u + (1-rho) d^2;  p -= lr d */
+size_t isa_adadelta_workspace_bytes(void);
+int isa_adadelta_step(float* param, const float* grad, float* square_avg, float* acc_delta, long long n, float lr, float rho, float eps,
+                      float weight_decay, float max_norm, float* norm_out, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

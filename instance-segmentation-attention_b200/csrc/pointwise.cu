@@ -302,6 +302,80 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused clip + Adadelta
+// The training step's `clip_grad_norm_` + `Adadelta.step` (/root/reference/code/lib/model.py:141-160, 271-281;
+// settings: OPTIMIZER = 'Adadelta', CLIP_GRAD_NORM = 10) over ONE flat parameter / gradient / state buffer: a
+// sum-of-squares pass (per-CTA double partials) and an update pass that first folds the partials in a fixed order
+// (every CTA gets the same norm, no host round trip) -- instead of ~45 multi-tensor launches (0.6 ms per step).
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, double* __restrict__ partial) {
+  __shared__ double s_w[8];
+  double acc = 0.0;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ld4(g + i * 4);
+    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[n4 * 4 + threadIdx.x]; acc += (double)v * v; }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+struct AdadeltaParams {
+  float* param; const float* grad; float* square_avg; float* acc_delta;
+  long long n;
+  float lr, rho, eps, weight_decay, max_norm;   // max_norm <= 0: no clipping
+  const double* partial; int n_partial;
+  float* norm_out;                              // total gradient norm before clipping (or null)
+};
+
+__device__ __forceinline__ void adadelta1(float& p, float g, float& sq, float& ad, const AdadeltaParams& a, float clip) {
+  g = g * clip;
+  if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+  sq = a.rho * sq + (1.f - a.rho) * g * g;
+  const float delta = sqrtf(ad + a.eps) / sqrtf(sq + a.eps) * g;
+  ad = a.rho * ad + (1.f - a.rho) * delta * delta;
+  p = p - a.lr * delta;
+}
+
+__global__ void __launch_bounds__(256) adadelta_step_kernel(const AdadeltaParams a) {
+  __shared__ float s_clip;
+  if (threadIdx.x == 0) {
+    float clip = 1.f;
+    if (a.max_norm > 0.f || a.norm_out) {
+      double t = 0.0;
+      for (int i = 0; i < a.n_partial; ++i) t += a.partial[i];
+      const float norm = (float)sqrt(t);
+      if (a.norm_out && blockIdx.x == 0) *a.norm_out = norm;
+      if (a.max_norm > 0.f) clip = fminf(a.max_norm / (norm + 1e-6f), 1.f);     // torch.nn.utils.clip_grad_norm_
+    }
+    s_clip = clip;
+  }
+  __syncthreads();
+  const float clip = s_clip;
+  const long long n4 = a.n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = ld4(a.param + i * 4), sq = ld4(a.square_avg + i * 4), ad = ld4(a.acc_delta + i * 4);
+    const float4 g = ld4(a.grad + i * 4);
+    adadelta1(p.x, g.x, sq.x, ad.x, a, clip); adadelta1(p.y, g.y, sq.y, ad.y, a, clip);
+    adadelta1(p.z, g.z, sq.z, ad.z, a, clip); adadelta1(p.w, g.w, sq.w, ad.w, a, clip);
+    *reinterpret_cast<float4*>(a.param + i * 4) = p;
+    *reinterpret_cast<float4*>(a.square_avg + i * 4) = sq;
+    *reinterpret_cast<float4*>(a.acc_delta + i * 4) = ad;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    adadelta1(a.param[i], a.grad[i], a.square_avg[i], a.acc_delta[i], a, clip);
+  }
+}
+
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -1226,6 +1300,46 @@ int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, 
   long long grid = (total4 + 255) / 256;
   if (grid > (long long)di.num_sms * 16) grid = (long long)di.num_sms * 16;
   maxpool2x2_bwd_kernel<<<(unsigned)grid, 256, 0, stream>>>(gy, idx, gx, total4, Ho, Wo, W, C4, (long long)H * W * C);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+// Workspace of isa_adadelta_step (per-CTA partial sums of squares).
+size_t isa_adadelta_workspace_bytes(void) {
+  IsaDeviceInfo di;
+  if (isa_device_info(&di)) return 0;
+  return (size_t)di.num_sms * 4 * sizeof(double);
+}
+
+// One optimizer step over flat fp32 buffers of n elements (16-byte aligned): optional global-norm clipping
+// (max_norm > 0; coefficient min(1, max_norm / (norm + 1e-6)) like torch.nn.utils.clip_grad_norm_), then PyTorch's
+// Adadelta update with L2 weight decay.  grad is read only; norm_out (device float, may be NULL) receives the norm.
+int isa_adadelta_step(float* param, const float* grad, float* square_avg, float* acc_delta, long long n, float lr, float rho, float eps,
+                      float weight_decay, float max_norm, float* norm_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ISA_CHECK_ARG(param && grad && square_avg && acc_delta && n > 0 && workspace, "adadelta_step: bad argument");
+  ISA_CHECK_ARG(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(square_avg) |
+                  reinterpret_cast<uintptr_t>(acc_delta)) & 15u) == 0, "adadelta_step: buffers must be 16-byte aligned");
+  if (workspace_bytes < isa_adadelta_workspace_bytes()) {
+    isa_set_error("adadelta_step: workspace too small");
+    return ISA_ERR_WORKSPACE;
+  }
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  long long grid = ((n >> 2) + 255) / 256;
+  if (grid < 1) grid = 1;
+  if (grid > (long long)di.num_sms * 4) grid = (long long)di.num_sms * 4;
+  double* partial = reinterpret_cast<double*>(workspace);
+  const bool need_norm = max_norm > 0.f || norm_out;
+  if (need_norm) {
+    sumsq_partial_kernel<<<(unsigned)grid, 256, 0, stream>>>(grad, n, partial);
+    ISA_CUDA(cudaGetLastError());
+  }
+  AdadeltaParams a;
+  a.param = param; a.grad = grad; a.square_avg = square_avg; a.acc_delta = acc_delta; a.n = n;
+  a.lr = lr; a.rho = rho; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+  a.partial = partial; a.n_partial = need_norm ? (int)grid : 0; a.norm_out = norm_out;
+  adadelta_step_kernel<<<(unsigned)grid, 256, 0, stream>>>(a);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }

@@ -169,3 +169,32 @@ def test_predict_many_equals_predict_array_and_prefetcher_is_lossless(cuda):
     for b, g in zip(batches, got):
         for t, u in zip(b, g):
             assert u.is_cuda and torch.equal(t, u.cpu())
+
+
+def test_cuda_graph_replay_equals_eager_steps(cuda):
+    """Model.enable_cuda_graph(): the captured step replays the same arithmetic as the eager step (costs of six steps on
+    alternating batches and the final parameters agree to fp32 noise: the loss forward uses float atomics)."""
+    batches = []
+    for seed in (5, 6):
+        d = synth.batch(seed, 2, 3, 64, 64, 32, n_min=2, n_max=5)
+        batches.append([torch.tensor(d["emb"], device=cuda),
+                        torch.tensor(np.stack([(d["labels"] == 255), (d["labels"] != 255)], 1).astype(np.int64), device=cuda),
+                        torch.tensor(synth.onehot(d["labels"], 32, np.int64), device=cuda),
+                        torch.tensor(d["n_objects"], device=cuda)])
+    runs = []
+    for graph in (False, True):
+        m = _make_model(cuda)
+        m.define_criterion(None, 0.5, 1.5, 2, False, 'Multi')
+        m.define_optimizer(1.0, 0.001, 0.5, 25, 'Adadelta')
+        if graph:
+            m.enable_cuda_graph(warmup_steps=2)
+        costs = []
+        for i in range(6):
+            b = batches[i % 2]
+            costs.append(float(m.train_step(b[0], b[1], b[2], b[3], 10.0)['Cost']))
+        if graph:
+            assert len(m._graphs) == 1
+        runs.append((costs, torch.cat([p.detach().reshape(-1) for p in m.model.parameters()]).clone()))
+    (c0, p0), (c1, p1) = runs
+    np.testing.assert_allclose(c1, c0, rtol=2e-4)
+    assert _rel(p1, p0) < 1e-3

@@ -144,3 +144,31 @@ def test_maxpool2x2_matches_torch(cuda, N, C, H, W):
     assert torch.equal(ga, gb)
     with torch.no_grad():
         assert torch.equal(torch.nan_to_num(MaxPool2x2()(x), nan=-7.0), torch.nan_to_num(yb, nan=-7.0))
+
+
+def test_fused_adadelta_matches_torch(cuda):
+    """clip_grad_norm_ + torch.optim.Adadelta vs the flat fused optimizer on the same parameters / gradients."""
+    from isa_b200.optim import FusedAdadelta
+    torch.manual_seed(5)
+    shapes = [(7, 3, 3, 3), (7,), (33, 17), (5,), (1,), (64, 64, 3, 3)]
+    pa = [nn.Parameter(torch.randn(*s, device=cuda)) for s in shapes]
+    pb = [nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdadelta(pa, lr=1.0, weight_decay=1e-3)
+    ob = torch.optim.Adadelta(pb, lr=1.0, weight_decay=1e-3)
+    for step in range(6):
+        clip = 10.0 if step % 2 == 0 else 0.5
+        oa.zero_grad()
+        ob.zero_grad()
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a) * (3.0 if step < 3 else 0.01)
+            a.grad.add_(g)                      # autograd accumulates in place into the flat views
+            b.grad = g.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_(pb, clip)
+        ob.step()
+        oa.step(clip_grad_norm=clip)
+        torch.testing.assert_close(oa.grad_norm[0], ref_norm, rtol=1e-5, atol=1e-6)
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(a.data, b.data, rtol=2e-5, atol=2e-6)
+    sd = oa.state_dict()
+    oa.load_state_dict(sd)
+    assert oa.param_groups[0]['lr'] == 1.0
