@@ -368,7 +368,7 @@ def run_ours(args):
         launches = sum(_lib.KERNELS_PER_CALL[k] * c for k, (c, _) in summ.items())
         # (b) value: inputs resident in HBM, the step replayed from its CUDA graph (Model.enable_cuda_graph: the same
         #     ~800 launches per step, submitted by one cudaGraphLaunch instead of one by one from Python)
-        use_graph = not args.no_graph and (world == 1 or os.environ.get("ISA_GRAPH_DDP") == "1")
+        use_graph = not args.no_graph
         if use_graph:
             model.enable_cuda_graph(warmup_steps=1)
         sampler.start()

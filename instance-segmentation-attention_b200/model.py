@@ -162,20 +162,30 @@ class Model(object):
             if seen < self._graph_warmup:
                 return None                          # eager warm-up (also cuDNN autotuning)
             static = [t.clone() for t in (images, sem, ins, nobj)]
+            # data parallel: NCCL collectives stay OUTSIDE the graph (captured collectives leave the process group's
+            # watchdog with events it can never complete: the process hangs at exit).  The q-regulariser's global
+            # denominator becomes a static input, the gradient all-reduce + update run eagerly after the replay.
+            static_q = torch.zeros(1, device=self.device, dtype=torch.float32) if self.distributed else None
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             timer_was = _lib.TIMER.enabled
             _lib.TIMER.enabled = False               # event-timed C-ABI calls cannot be captured
             try:
                 with torch.cuda.graph(graph):
-                    out = self.__eager_step(static[0], static[1], static[2], static[3], clip_grad_norm, criterion_type, True)
+                    out = self.__fwd_bwd(static[0], static[1], static[2], static[3], criterion_type, True, static_q)
+                    if not self.distributed:
+                        self.__update(clip_grad_norm)
             finally:
                 _lib.TIMER.enabled = timer_was
-            g = self._graphs[key] = (graph, static, out)
-        graph, static, out = g
+            g = self._graphs[key] = (graph, static, static_q, out)
+        graph, static, static_q, out = g
         for dst, src in zip(static, (images, sem, ins, nobj)):
             dst.copy_(src, non_blocking=True)
+        if static_q is not None:
+            static_q.copy_(self.__q_denominator(ins), non_blocking=True)
         graph.replay()
+        if self.distributed:
+            self.__update(clip_grad_norm)
         return out
 
     # ------------------------------------------------------------------ one step (model.py:162-281)
@@ -194,9 +204,15 @@ class Model(object):
         return self.__eager_step(images, sem_seg_annotations, ins_seg_annotations, n_objects, clip_grad_norm, criterion_type, training)
 
     def __eager_step(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, clip_grad_norm, criterion_type, training):
-        """images (b,c,h,w) float; sem one-hot (b,n_classes,h,w); ins one-hot (b,K,h,w) (float/int64/uint8) or
-        a (b,h,w) uint8 label map; n_objects (b,).  CPU tensors are copied with non_blocking=True as the
-        reference does (.cuda(async=True)).  Returns the metrics dict of model.py:242-269 (device scalars)."""
+        dev = self.device
+        ins = ins_seg_annotations.to(dev, non_blocking=True)
+        out_metrics = self.__fwd_bwd(images, sem_seg_annotations, ins, n_objects, criterion_type, training, self.__q_denominator(ins))
+        if training:
+            self.__update(clip_grad_norm)
+        return out_metrics
+
+    def __fwd_bwd(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, criterion_type, training, q_den):
+        """Forward, losses and (training) zero_grad + backward; returns the metrics dict of model.py:242-269."""
         self.model.train(training)
         dev = self.device
         images = images.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
@@ -209,7 +225,7 @@ class Model(object):
             cost = 0
             if self.use_instance_segmentation:
                 ins_cost, _means = self.criterion_discriminative(ins_seg_predictions, ins, nobj, self.max_n_objects,
-                                                                 q_denominator=self.__q_denominator(ins))
+                                                                 q_denominator=q_den)
                 cost = cost + ins_cost
                 out_metrics['INS Cost'] = ins_cost.detach()
             if criterion_type in ['CE', 'Multi']:
@@ -223,23 +239,25 @@ class Model(object):
                 out_metrics['Dice Cost'] = dice_cost.detach()
             out_metrics['Cost'] = cost.detach()
         if training:
-            fused = hasattr(self.optimizer, 'flat_grad')
-            if fused:
+            if hasattr(self.optimizer, 'flat_grad'):
                 self.optimizer.zero_grad()
             elif self._flat_grad is not None:
                 self._flat_grad.zero()
             else:
                 self.model.zero_grad()
             cost.backward()
-            if self.distributed:
-                self.__allreduce_gradients()
-            if fused:
-                self.optimizer.step(clip_grad_norm=clip_grad_norm)
-            else:
-                if clip_grad_norm != 0:
-                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip_grad_norm)
-                self.optimizer.step()
         return out_metrics
+
+    def __update(self, clip_grad_norm):
+        """Gradient all-reduce (data parallel), global-norm clipping and the optimizer step (model.py:271-281)."""
+        if self.distributed:
+            self.__allreduce_gradients()
+        if hasattr(self.optimizer, 'flat_grad'):
+            self.optimizer.step(clip_grad_norm=clip_grad_norm)
+        else:
+            if clip_grad_norm != 0:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip_grad_norm)
+            self.optimizer.step()
 
     # ------------------------------------------------------------------ fit (model.py:358-464)
     def fit(self, criterion_type, delta_var, delta_dist, norm, learning_rate, weight_decay, clip_grad_norm,
