@@ -46,7 +46,7 @@ def _loss_ref_label_map(emb, labels, n_obj):
     qreg = ((l - 1.0) ** 2).sum() / int(fgm.sum())
     loss = var + 0.005 * qreg
     loss.backward()
-    return float(loss), mu.detach().numpy(), x.grad.T.reshape(emb.shape).numpy()
+    return float(loss.detach()), mu.detach().numpy(), x.grad.T.reshape(emb.shape).numpy()
 
 
 def test_discriminative_loss_full_size(cuda, scene):
