@@ -145,8 +145,8 @@ class Model(object):
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def enable_cuda_graph(self, warmup_steps=3):
-        """Capture the whole training step (forward, losses, backward, gradient all-reduce, clip + Adadelta: ~800
-        launches at batch 16) in ONE CUDA graph per input signature after `warmup_steps` eager steps (cuDNN's algorithm
+        """Capture the training step's forward, losses and backward (~800 launches at batch 16; the gradient all-reduce
+        and the two launches of the fused clip + Adadelta update stay eager) in ONE CUDA graph per input signature after `warmup_steps` eager steps (cuDNN's algorithm
         search runs in those), then replay it: the step is launch-bound on the host otherwise (kernels 12.0 ms of a
         13.3 ms step).  Needs device-resident inputs of a fixed shape and the fused optimizer; anything else silently
         takes the eager path.  Metrics come back as the graph's static device scalars."""
@@ -162,9 +162,11 @@ class Model(object):
             if seen < self._graph_warmup:
                 return None                          # eager warm-up (also cuDNN autotuning)
             static = [t.clone() for t in (images, sem, ins, nobj)]
-            # data parallel: NCCL collectives stay OUTSIDE the graph (captured collectives leave the process group's
-            # watchdog with events it can never complete: the process hangs at exit).  The q-regulariser's global
-            # denominator becomes a static input, the gradient all-reduce + update run eagerly after the replay.
+            # The graph holds forward + losses + backward.  The tail stays eager: (i) NCCL collectives captured in a
+            # graph leave the process group's watchdog with events it can never complete (the process hangs at exit),
+            # so the q-regulariser's global denominator is a static input and the gradient all-reduce runs after the
+            # replay; (ii) the optimizer's learning rate is a kernel ARGUMENT that ReduceLROnPlateau changes between
+            # epochs, so the two launches of the fused clip + Adadelta update are issued eagerly too.
             static_q = torch.zeros(1, device=self.device, dtype=torch.float32) if self.distributed else None
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
@@ -173,8 +175,6 @@ class Model(object):
             try:
                 with torch.cuda.graph(graph):
                     out = self.__fwd_bwd(static[0], static[1], static[2], static[3], criterion_type, True, static_q)
-                    if not self.distributed:
-                        self.__update(clip_grad_norm)
             finally:
                 _lib.TIMER.enabled = timer_was
             g = self._graphs[key] = (graph, static, static_q, out)
@@ -184,8 +184,7 @@ class Model(object):
         if static_q is not None:
             static_q.copy_(self.__q_denominator(ins), non_blocking=True)
         graph.replay()
-        if self.distributed:
-            self.__update(clip_grad_norm)
+        self.__update(clip_grad_norm)
         return out
 
     # ------------------------------------------------------------------ one step (model.py:162-281)
