@@ -27,6 +27,7 @@ parser.add_argument('--nworkers', type=int, default=2)
 parser.add_argument('--dataset', type=str, default='CVPPP')
 parser.add_argument('--output', default='models', help='Directory for checkpoints and logs')
 parser.add_argument('--synthetic', type=int, default=8, help='Number of synthetic minibatches per epoch')
+parser.add_argument('--cuda_graph', action='store_true', help='Replay forward+backward of the training step from a CUDA graph (fixed batch shape)')
 
 
 class SyntheticLoader(object):
@@ -60,6 +61,8 @@ if __name__ == '__main__':
                   use_instance_segmentation=ts.USE_INSTANCE_SEGMENTATION, use_coords=ts.USE_COORDINATES,
                   load_model_path=opt.model, usegpu=True, n_embedding=ts.D_MODEL, distributed=world > 1,
                   device=torch.device('cuda', local_rank))
+    if opt.cuda_graph:
+        model.enable_cuda_graph()
     train_loader = SyntheticLoader(opt.synthetic, opt.batchsize, ts, 1000 * rank)
     test_loader = SyntheticLoader(max(1, opt.synthetic // 4), opt.batchsize, ts, 500000 + 1000 * rank)
     model.fit(ts.CRITERION, ts.DELTA_VAR, ts.DELTA_DIST, ts.NORM, ts.LEARNING_RATE, ts.WEIGHT_DECAY, ts.CLIP_GRAD_NORM,
