@@ -41,7 +41,24 @@ __global__ void __launch_bounds__(kThreads) bias_act_fwd_kernel(float* __restric
   float b[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) b[i] = __ldg(bias + c + i);
-  for (long long r = (long long)blockIdx.x * rpi + t / cv; r < rows; r += (long long)gridDim.x * rpi) {
+  const long long step = (long long)gridDim.x * rpi;
+  long long r = (long long)blockIdx.x * rpi + t / cv;
+  if (V == 4) {
+    // four independent rows per iteration: the loads are issued together (in-place update: the compiler may not hoist
+    // a load above the previous row's store on its own)
+    for (; r + 3 * step < rows; r += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ld4(x + (r + j * step) * C + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j].x += b[0]; v[j].y += b[1 % V]; v[j].z += b[2 % V]; v[j].w += b[3 % V];
+        if (RELU) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
+        *reinterpret_cast<float4*>(x + (r + j * step) * C + c) = v[j];
+      }
+    }
+  }
+  for (; r < rows; r += step) {
     float* p = x + r * C + c;
     if (V == 4) {
       float4 v = ld4(p);
@@ -70,7 +87,31 @@ __global__ void __launch_bounds__(kThreads) bias_act_bwd_kernel(const float* __r
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
   if (active) {
-    for (long long r = (long long)blockIdx.x * rpi + t / cv; r < rows; r += (long long)gridDim.x * rpi) {
+    const long long step = (long long)gridDim.x * rpi;
+    long long r = (long long)blockIdx.x * rpi + t / cv;
+    if (V == 4) {
+      // two independent rows per iteration (four 16-byte loads in flight per thread)
+      for (; r + step < rows; r += 2 * step) {
+        float4 g[2], yy[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const long long o = (r + j * step) * C + c;
+          g[j] = ld4(gy + o);
+          if (RELU) yy[j] = ld4(y + o);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const long long o = (r + j * step) * C + c;
+          if (RELU) {
+            g[j].x = yy[j].x > 0.f ? g[j].x : 0.f; g[j].y = yy[j].y > 0.f ? g[j].y : 0.f;
+            g[j].z = yy[j].z > 0.f ? g[j].z : 0.f; g[j].w = yy[j].w > 0.f ? g[j].w : 0.f;
+          }
+          if (gx) *reinterpret_cast<float4*>(gx + o) = g[j];
+          acc[0] += g[j].x; acc[1 % V] += g[j].y; acc[2 % V] += g[j].z; acc[3 % V] += g[j].w;
+        }
+      }
+    }
+    for (; r < rows; r += step) {
       const long long o = r * C + c;
       if (V == 4) {
         float4 g = ld4(gy + o);
