@@ -145,8 +145,9 @@ _LN_WIDTHS = (8, 16, 24, 32, 40, 48, 64)
 
 def add_layer_norm(x, res, ln):
     """ln(x + res) for an nn.LayerNorm `ln` over the last dimension (fused kernel for the widths it is built for)."""
+    _lib.require_cuda(x, "activation")          # no CPU fallback: other widths / dtypes use the library op ON THE GPU
     C = x.shape[-1]
-    if (x.is_cuda and x.dtype == torch.float32 and C in _LN_WIDTHS and ln.elementwise_affine and ln.bias is not None
+    if (x.dtype == torch.float32 and C in _LN_WIDTHS and ln.elementwise_affine and ln.bias is not None
             and tuple(ln.normalized_shape) == (C,) and x.shape == res.shape):
         return _AddLayerNormFn.apply(x, res, ln.weight, ln.bias, ln.eps)
     return ln(x + res)
@@ -294,7 +295,8 @@ class MaxPool2x2(nn.Module):
     the library op."""
 
     def forward(self, x):
-        if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2
+        _lib.require_cuda(x, "activation")      # no CPU fallback: other layouts use the library op ON THE GPU
+        if (x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2
                 and x.is_contiguous(memory_format=torch.channels_last)):
             return _MaxPool2x2Fn.apply(x)
         return F.max_pool2d(x, 2, 2)
