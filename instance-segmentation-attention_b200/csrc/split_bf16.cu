@@ -69,15 +69,15 @@ __global__ void __launch_bounds__(256) split_bf16x3_rows_kernel(const SplitParam
   if (t >= rpi * c4) return;
   const int c = (t % c4) << 2;
   const long long rstep = (long long)gridDim.x * rpi;
-#pragma unroll 2
-  for (long long r = (long long)blockIdx.x * rpi + t / c4; r < p.rows; r += rstep) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_row = [&](long long r) -> float4 {
     bool ok = true;
     if (p.pos_step != 0) {
       const int pos = (int)((r / p.pos_div) % p.pos_mod) + p.pos_step;
       ok = pos >= 0 && pos < p.pos_mod;
     }
-    if (ok) v = __ldg(reinterpret_cast<const float4*>(p.src + (r + p.shift) * p.src_ld + c));
+    return ok ? __ldg(reinterpret_cast<const float4*>(p.src + (r + p.shift) * p.src_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto store_row = [&](long long r, const float4 v) {
     __nv_bfloat16 h[4], l[4];
     split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
     uint2 hv, lv;
@@ -89,7 +89,17 @@ __global__ void __launch_bounds__(256) split_bf16x3_rows_kernel(const SplitParam
     *reinterpret_cast<uint2*>(d0) = hv;
     *reinterpret_cast<uint2*>(d0 + p.part_stride) = p.order == 0 ? hv : lv;
     *reinterpret_cast<uint2*>(d0 + 2 * p.part_stride) = p.order == 0 ? lv : hv;
+  };
+  long long r = (long long)blockIdx.x * rpi + t / c4;
+  // four independent rows per iteration: the loads are issued together before any store
+  for (; r + 3 * rstep < p.rows; r += 4 * rstep) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = load_row(r + j * rstep);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_row(r + j * rstep, v[j]);
   }
+  for (; r < p.rows; r += rstep) store_row(r, load_row(r));
 }
 
 }  // namespace
