@@ -39,7 +39,12 @@ if __name__ == '__main__':
         fg_seg_pred = np.array(Image.open(os.path.join(opt.pred_dir, name, name + '-fg_mask.png')))
         fg_seg_gt = (fg_seg_gt == 1).astype('bool')
         fg_seg_pred = (fg_seg_pred == 255).astype('bool')
-        sbds.append(calc_sbd(ins_seg_gt, ins_seg_pred))
+        if ins_seg_pred.max() == 0 or ins_seg_gt.max() == 0:
+            # no predicted (or no annotated) instance: the reference's np.max([]) raises here (evaluate.py:31-38); an image
+            # that could not be clustered (pred_list.py writes an empty mask for it) scores 0 instead of aborting the run
+            sbds.append(0.0)
+        else:
+            sbds.append(calc_sbd(ins_seg_gt, ins_seg_pred))
         dics.append(calc_dic(n_objects_gt, n_objects_pred))
         fg_dices.append(calc_dice(fg_seg_gt, fg_seg_pred))
     print('MEAN SBD     : ', np.mean(sbds))
