@@ -35,7 +35,9 @@ if __name__ == '__main__':
             kept.append(r)
             yield r
 
+    written = 0
     for image_name, (fg_seg_pred, ins_seg_pred, n_objects_pred) in zip(image_names, prediction.predict_many(tee())):
         image = kept.pop(0)
         _common.write_prediction(os.path.join(opt.output, image_name), image_name, image, fg_seg_pred, ins_seg_pred, n_objects_pred)
-    print('wrote %d predictions under %s' % (len(image_names), opt.output))
+        written += 1
+    print('wrote %d of %d predictions under %s' % (written, len(image_names), opt.output))

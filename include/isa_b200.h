@@ -86,10 +86,14 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
                       float* grad_emb, void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 /* Dense one-hot masks (kind 1..3) -> u8 label map; *not_onehot_flag (device int) is set to 1
- * when some pixel has several non-zeros or a weight other than 1.
+ * when some pixel has several non-zeros or a weight other than 1; *fg_count (device u64, may be NULL) receives the
+ * number of foreground pixels = int(sum(target)) of discriminative.py:153-159 for a one-hot target, so the data-parallel
+ * q-regulariser denominator needs no second pass over the masks.
  * Replaces the int64 one-hot expansion of lib/dataset.py:354-376 on the device side. */
 int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int H, int W,
-                         unsigned char* labels, int* not_onehot_flag, isa_stream_t stream);
+                         unsigned char* labels, int* not_onehot_flag, unsigned long long* fg_count, isa_stream_t stream);
+/* Foreground pixels (label < K) of a u8 label map [total] -> *fg_count (device u64). */
+int isa_label_fg_count(const unsigned char* labels, long long total, int K, unsigned long long* fg_count, isa_stream_t stream);
 
 /* ------------------------------------------------------------------ embedding clustering
  * Replaces sklearn.cluster.KMeans(n_clusters=k, n_init=35, max_iter=500).fit_predict(X) as called by
@@ -307,6 +311,32 @@ int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, 
 size_t isa_adadelta_workspace_bytes(void);
 int isa_adadelta_step(float* param, const float* grad, float* square_avg, float* acc_delta, long long n, float lr, float rho, float eps,
                       float weight_decay, float max_norm, float* norm_out, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ fused semantic-head losses (cross entropy + Dice)
+ * Replaces, on the training step,
+ *   /root/reference/code/lib/losses/dice.py:10-51 (dice_coefficient), :54-89 (dice_loss, mean reduction) and the
+ *   CrossEntropyLoss(class_weights) call of /root/reference/code/lib/model.py:255-263
+ * with one forward and one backward pass over the logits.
+ * logits        [bs][n_classes][HW] f32 (NCHW planes), 2 <= n_classes <= 8
+ * class_map     [bs][HW] u8 class index per pixel (isa_onehot_argmax distils the collate's one-hot once)
+ * class_weights [n_classes] f32 or NULL (the same vector weights both losses, model.py:113-127)
+ * dice_time     1: den = sum p + sum t (what Model passes, model.py:264);  2: sum p^2 + sum t^2
+ * out_ce_dice   [2] f32: weighted-mean cross entropy, mean Dice loss (background dropped unless optimize_bg)
+ * workspace     isa_seg_losses_workspace_bytes bytes; hand the SAME buffer to isa_seg_losses_bwd.
+ * Deterministic (fixed-order partial sums, no float atomics). */
+size_t isa_seg_losses_workspace_bytes(int bs, int n_classes, long long HW);
+int isa_seg_losses_fwd(const float* logits, const unsigned char* class_map, const float* class_weights,
+                       int bs, int n_classes, long long HW, int dice_time, float smooth, int optimize_bg,
+                       float* out_ce_dice, void* workspace, size_t workspace_bytes, isa_stream_t stream);
+/* grad_ce / grad_dice: device scalars (NULL = 0); grad_logits [bs][n_classes][HW] out. */
+int isa_seg_losses_bwd(const float* logits, const unsigned char* class_map, const float* class_weights,
+                       int bs, int n_classes, long long HW, int dice_time, const float* grad_ce,
+                       const float* grad_dice, float* grad_logits, const void* workspace, size_t workspace_bytes,
+                       isa_stream_t stream);
+/* Dense one-hot [bs][n_classes][HW] (target_kind 1 f32, 2 i64, 3 u8) -> u8 class map, first maximum wins
+ * (Tensor.max(1)[1], model.py:256-257). */
+int isa_onehot_argmax(const void* target, int target_kind, int bs, int n_classes, long long HW,
+                      unsigned char* class_map, isa_stream_t stream);
 
 #ifdef __cplusplus
 }

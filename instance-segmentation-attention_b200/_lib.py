@@ -45,7 +45,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_onehot_to_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                     c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "isa_label_fg_count": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     # clustering
     "isa_kmeans_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "isa_kmeans_fit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_double,
@@ -111,6 +112,13 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_split_bf16x3": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_longlong,
                                  c_longlong, c_int, c_longlong, c_int, c_int, c_int, c_void_p]),
+    # fused semantic-head losses
+    "isa_seg_losses_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
+    "isa_seg_losses_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_seg_losses_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_onehot_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p]),
 }
 
 
@@ -120,7 +128,7 @@ class IsaError(RuntimeError):
 
 # kernels launched per C-ABI call (memsets and copies not counted); used by bench.py's gpu_launches
 KERNELS_PER_CALL = {
-    "isa_disc_loss_fwd": 2, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1,
+    "isa_disc_loss_fwd": 2, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1, "isa_label_fg_count": 1,
     "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
     "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 3,
     "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1, "isa_split_bf16x3": 1,
@@ -129,6 +137,7 @@ KERNELS_PER_CALL = {
     "isa_bias_act_fwd": 1, "isa_bias_act_bwd": 2, "isa_add_layernorm_fwd": 1, "isa_add_layernorm_bwd": 2,
     "isa_pixel_heads_fwd": 1, "isa_pixel_heads_bwd": 1, "isa_pixel_heads_wgrad": 2,
     "isa_maxpool2x2_fwd": 1, "isa_maxpool2x2_bwd": 1, "isa_adadelta_step": 2,
+    "isa_seg_losses_fwd": 1, "isa_seg_losses_bwd": 1, "isa_onehot_argmax": 1,
 }
 
 

@@ -663,15 +663,30 @@ __global__ void __launch_bounds__(kThreads) disc_bwd_kernel(const BwdParams prm)
 // Dense one-hot mask -> u8 label map (255 = background); *flag |= 1 if some
 // pixel is not one-hot (several non-zeros, or a value other than 1).
 template <int KIND>
-__global__ void onehot_to_labels_kernel(const void* __restrict__ tgt, unsigned char* __restrict__ labels, int bs, int K, int P, int* flag) {
+__global__ void onehot_to_labels_kernel(const void* __restrict__ tgt, unsigned char* __restrict__ labels, int bs, int K, int P, int* flag,
+                                        unsigned long long* fg_count) {
   const size_t total = (size_t)bs * P;
+  unsigned cnt = 0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / P), p = (int)(i % P);
     int k1; float w1, fg;
     const int nnz = read_mask<KIND>(tgt, (size_t)b * P, p, P, K, k1, w1, fg);
     labels[i] = (nnz >= 1) ? (unsigned char)k1 : (unsigned char)255;
+    cnt += (nnz >= 1);
     if (nnz > 1 || (nnz == 1 && w1 != 1.f)) atomicOr(flag, 1);
   }
+  if (fg_count) {   // integer atomics: order independent, deterministic
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(fg_count, (unsigned long long)cnt);
+  }
+}
+
+// foreground pixels (label < K) of a u8 label map
+__global__ void label_fg_count_kernel(const unsigned char* __restrict__ labels, size_t total, int K, unsigned long long* fg_count) {
+  unsigned cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) cnt += (labels[i] < K);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(fg_count, (unsigned long long)cnt);
 }
 
 int allow_smem(const void* fn, size_t smem) {
@@ -729,13 +744,13 @@ int launch_bwd(const BwdParams& prm, dim3 grid, size_t smem, cudaStream_t stream
 }
 
 int launch_onehot_to_labels(const void* target, int target_kind, int bs, int K, int P, unsigned char* labels, int* flag, int num_sms,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, unsigned long long* fg_count = nullptr) {
   const size_t total = (size_t)bs * P;
   int grid = (int)((total + 255) / 256);
   if (grid > num_sms * 16) grid = num_sms * 16;
-  if (target_kind == TGT_DENSE_F32) onehot_to_labels_kernel<TGT_DENSE_F32><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag);
-  else if (target_kind == TGT_DENSE_I64) onehot_to_labels_kernel<TGT_DENSE_I64><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag);
-  else onehot_to_labels_kernel<TGT_DENSE_U8><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag);
+  if (target_kind == TGT_DENSE_F32) onehot_to_labels_kernel<TGT_DENSE_F32><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag, fg_count);
+  else if (target_kind == TGT_DENSE_I64) onehot_to_labels_kernel<TGT_DENSE_I64><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag, fg_count);
+  else onehot_to_labels_kernel<TGT_DENSE_U8><<<grid, 256, 0, stream>>>(target, labels, bs, K, P, flag, fg_count);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }
@@ -868,7 +883,7 @@ int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, con
 }
 
 int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int H, int W,
-                         unsigned char* labels, int* not_onehot_flag, cudaStream_t stream) {
+                         unsigned char* labels, int* not_onehot_flag, unsigned long long* fg_count, cudaStream_t stream) {
   ISA_CHECK_ARG(target_kind >= 1 && target_kind <= 3, "onehot_to_labels: target_kind %d is not a dense kind (1..3)", target_kind);
   ISA_CHECK_ARG(target && labels && not_onehot_flag, "onehot_to_labels: null pointer");
   ISA_CHECK_ARG(bs > 0 && K > 0 && K <= 254 && H > 0 && W > 0, "onehot_to_labels: bad dimensions");
@@ -876,7 +891,21 @@ int isa_onehot_to_labels(const void* target, int target_kind, int bs, int K, int
   int rc = isa_device_info(&di);
   if (rc) return rc;
   ISA_CUDA(cudaMemsetAsync(not_onehot_flag, 0, sizeof(int), stream));
-  return launch_onehot_to_labels(target, target_kind, bs, K, H * W, labels, not_onehot_flag, di.num_sms, stream);
+  if (fg_count) ISA_CUDA(cudaMemsetAsync(fg_count, 0, sizeof(unsigned long long), stream));
+  return launch_onehot_to_labels(target, target_kind, bs, K, H * W, labels, not_onehot_flag, di.num_sms, stream, fg_count);
+}
+
+int isa_label_fg_count(const unsigned char* labels, long long total, int K, unsigned long long* fg_count, cudaStream_t stream) {
+  ISA_CHECK_ARG(labels && fg_count && total > 0 && K > 0 && K <= 255, "label_fg_count: bad argument");
+  IsaDeviceInfo di;
+  int rc = isa_device_info(&di);
+  if (rc) return rc;
+  ISA_CUDA(cudaMemsetAsync(fg_count, 0, sizeof(unsigned long long), stream));
+  long long grid = (total + 1023) / 1024;
+  if (grid > di.num_sms * 8) grid = di.num_sms * 8;
+  label_fg_count_kernel<<<(int)grid, 256, 0, stream>>>(labels, (size_t)total, K, fg_count);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
 }
 
 }  // extern "C"

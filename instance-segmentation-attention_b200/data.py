@@ -7,7 +7,43 @@ stream while the step of batch i computes (298 MB of int64 one-hot masks per 16-
 more than half a training step).  Every batch is still copied exactly once, from pinned host memory when the loader
 provides it (non-pinned tensors are pinned here first).
 """
+import numpy as np
 import torch
+
+
+def instance_label_map(instance_annotation, n_objects=None):
+    """(h,w,n) uint8 per-instance masks, as the reference's LMDB stores them and its collate pads them
+    (lib/dataset.py:36-58, :292-313) -> (h,w) uint8 label map, 255 = background.  1 byte per pixel instead of the
+    8*MAX_N_OBJECTS bytes of the collate's int64 one-hot."""
+    a = np.asarray(instance_annotation)
+    if n_objects is not None:
+        a = a[:, :, :int(n_objects)]
+    if a.shape[2] == 0:
+        return np.full(a.shape[:2], 255, dtype=np.uint8)
+    lab = a.argmax(axis=2).astype(np.uint8)
+    lab[a.max(axis=2) == 0] = 255
+    return lab
+
+
+def compact_collate(batch):
+    """Collate for per-sample tuples (image (c,h,w) float tensor, semantic (h,w) uint8 class map, instance (h,w,n) uint8
+    masks, n_objects) -- the items the reference's AlignCollate.__preprocess returns (lib/dataset.py:322) -- that emits
+    what the kernels read: (images (b,c,h,w), sem (b,h,w) uint8 class map, ins (b,h,w) uint8 label map, n_objects).
+    Replaces the int64 one-hot expansion of lib/dataset.py:354-376: 15 MB instead of 298 MB per 16-image batch."""
+    images, sems, inss, nobj = zip(*batch)
+    images = torch.stack([torch.as_tensor(i) for i in images])
+    sem = torch.from_numpy(np.stack([np.asarray(s, dtype=np.uint8) for s in sems]))
+    ins = torch.from_numpy(np.stack([instance_label_map(a, n) for a, n in zip(inss, nobj)]))
+    return images, sem, ins, torch.IntTensor([int(n) for n in nobj])
+
+
+def to_compact(sem_one_hot, ins_one_hot):
+    """Reference-format HOST targets (one-hot (b,n_classes,h,w), (b,K,h,w)) -> (uint8 class map, uint8 label map)."""
+    sem = sem_one_hot.max(1)[1].to(torch.uint8)
+    val, idx = ins_one_hot.max(1)
+    ins = idx.to(torch.uint8)
+    ins[val == 0] = 255
+    return sem, ins
 
 
 class CudaPrefetcher(object):

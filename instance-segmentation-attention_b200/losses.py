@@ -131,8 +131,8 @@ class DiscriminativeLoss(_Loss):
         return loss, means
 
 
-def onehot_to_labels(target):
-    """(bs,K,H,W) one-hot masks -> ((bs,H,W) uint8 label map, device int flag `not_onehot`)."""
+def onehot_to_labels(target, with_count=False):
+    """(bs,K,H,W) one-hot masks -> ((bs,H,W) uint8 label map, device int flag `not_onehot`[, device int64 fg count])."""
     lib = _lib.load()
     _lib.require_cuda(target, "target")
     kind = _target_kind(target, None)
@@ -144,7 +144,19 @@ def onehot_to_labels(target):
     bs, K, H, W = tgt.shape
     labels = torch.empty(bs, H, W, device=tgt.device, dtype=torch.uint8)
     flag = torch.empty(1, device=tgt.device, dtype=torch.int32)
-    rc = lib.isa_onehot_to_labels(_lib.ptr(tgt), kind, bs, K, H, W, _lib.ptr(labels), _lib.ptr(flag),
+    count = torch.empty(1, device=tgt.device, dtype=torch.int64) if with_count else None
+    rc = lib.isa_onehot_to_labels(_lib.ptr(tgt), kind, bs, K, H, W, _lib.ptr(labels), _lib.ptr(flag), _lib.ptr(count),
                                   _lib.stream_ptr(tgt.device))
     _lib.check(rc, "isa_onehot_to_labels")
-    return labels, flag
+    return (labels, flag, count) if with_count else (labels, flag)
+
+
+def label_fg_count(labels, K):
+    """Foreground pixels (label < K) of a uint8 label map -> 1-element device int64 tensor."""
+    lib = _lib.load()
+    _lib.require_cuda(labels, "labels")
+    lab = labels.contiguous()
+    count = torch.empty(1, device=lab.device, dtype=torch.int64)
+    rc = lib.isa_label_fg_count(_lib.ptr(lab), lab.numel(), int(K), _lib.ptr(count), _lib.stream_ptr(lab.device))
+    _lib.check(rc, "isa_label_fg_count")
+    return count

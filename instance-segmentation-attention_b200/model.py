@@ -28,8 +28,8 @@ from torch.optim.lr_scheduler import ReduceLROnPlateau
 
 from . import _lib, parallel
 from .archs import ReSeg
-from .losses import DiscriminativeLoss
-from .seg_losses import DiceLoss
+from .losses import DiscriminativeLoss, label_fg_count, onehot_to_labels
+from .seg_losses import DiceLoss, SegLosses, class_map
 
 
 class Model(object):
@@ -101,6 +101,8 @@ class Model(object):
             self.criterion_ce = torch.nn.CrossEntropyLoss(w)
         if criterion in ['Dice', 'Multi']:
             self.criterion_dice = DiceLoss(optimize_bg=optimize_bg, weight=w, smooth=smooth)
+        # what the step runs: cross entropy + Dice of the semantic head in one fused pass (csrc/seg_losses.cu)
+        self.criterion_seg = SegLosses(w, optimize_bg=optimize_bg, smooth=smooth)
         self.criterion_type = criterion
 
     def define_optimizer(self, learning_rate, weight_decay, lr_drop_factor, lr_drop_patience, optimizer='Adam'):
@@ -133,15 +135,23 @@ class Model(object):
             self._flat_grad = parallel.FlatGradBucket(self.model.parameters())
         self._flat_grad.allreduce(average=True)
 
-    def __q_denominator(self, ins):
-        """Global foreground count / world size (see parallel.py); None on a single process."""
+    def __compact_targets(self, sem, ins):
+        """Reference-format targets -> what the kernels read, ONE pass over the dense masks:
+        sem one-hot (b,n_classes,h,w) -> uint8 class map (b,h,w);  ins one-hot int64/uint8 (b,K,h,w) -> uint8 label map
+        (b,h,w), 255 = background (float masks may be soft: they stay dense);  uint8 maps pass through.  Also returns the
+        data-parallel q-regulariser denominator (global foreground count / world size; None on a single process) -- the
+        count comes out of the same distillation pass, nothing re-reads the masks."""
+        dev = self.device
+        sem_map = class_map(sem.to(dev, non_blocking=True))
+        ins = ins.to(dev, non_blocking=True)
+        count = None
+        if ins.dim() == 4 and ins.dtype in (torch.int64, torch.uint8, torch.bool):
+            ins, _flag, count = onehot_to_labels(ins, with_count=True)
         if not self.distributed:
-            return None
-        if ins.dim() == 3:
-            local = (ins < self.max_n_objects).sum()
-        else:
-            local = ins.sum()
-        return parallel.global_q_denominator(local)
+            return sem_map, ins, None
+        if count is None:
+            count = label_fg_count(ins, self.max_n_objects) if ins.dim() == 3 else ins.sum()
+        return sem_map, ins, parallel.global_q_denominator(count)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def enable_cuda_graph(self, warmup_steps=3):
@@ -152,7 +162,8 @@ class Model(object):
         takes the eager path.  Metrics come back as the graph's static device scalars."""
         self._graph_warmup = max(int(warmup_steps), 1)
 
-    def __graph_step(self, images, sem, ins, nobj, clip_grad_norm, criterion_type):
+    def __graph_step(self, images, sem, ins, nobj, q_den, clip_grad_norm, criterion_type):
+        """sem / ins are the COMPACT targets (uint8 maps, or dense float masks)."""
         key = (tuple(images.shape), tuple(sem.shape), sem.dtype, tuple(ins.shape), ins.dtype, tuple(nobj.shape), nobj.dtype,
                float(clip_grad_norm), criterion_type)
         g = self._graphs.get(key)
@@ -182,7 +193,7 @@ class Model(object):
         for dst, src in zip(static, (images, sem, ins, nobj)):
             dst.copy_(src, non_blocking=True)
         if static_q is not None:
-            static_q.copy_(self.__q_denominator(ins), non_blocking=True)
+            static_q.copy_(q_den, non_blocking=True)
         graph.replay()
         self.__update(clip_grad_norm)
         return out
@@ -190,34 +201,30 @@ class Model(object):
     # ------------------------------------------------------------------ one step (model.py:162-281)
     def train_step(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, clip_grad_norm=10.0,
                    criterion_type=None, mode='training'):
-        """images (b,c,h,w) float; sem one-hot (b,n_classes,h,w); ins one-hot (b,K,h,w) (float/int64/uint8) or
-        a (b,h,w) uint8 label map; n_objects (b,).  CPU tensors are copied with non_blocking=True as the
-        reference does (.cuda(async=True)).  Returns the metrics dict of model.py:242-269 (device scalars)."""
+        """images (b,c,h,w) float; sem one-hot (b,n_classes,h,w) or a (b,h,w) uint8 class map; ins one-hot (b,K,h,w)
+        (float/int64/uint8) or a (b,h,w) uint8 label map (255 = background); n_objects (b,).  CPU tensors are copied with
+        non_blocking=True as the reference does (.cuda(async=True)).  Returns the metrics dict of model.py:242-269
+        (device scalars)."""
         criterion_type = criterion_type or self.criterion_type
         training = mode == 'training'
-        if (training and self._graph_warmup > 0 and hasattr(self.optimizer, 'flat_grad') and not _lib.TIMER.enabled
-                and all(torch.is_tensor(t) and t.is_cuda for t in (images, sem_seg_annotations, ins_seg_annotations, n_objects))):
-            out = self.__graph_step(images, sem_seg_annotations, ins_seg_annotations, n_objects.reshape(-1), clip_grad_norm, criterion_type)
+        dev = self.device
+        images = images.to(dev, non_blocking=True)
+        sem, ins, q_den = self.__compact_targets(sem_seg_annotations, ins_seg_annotations)
+        nobj = torch.as_tensor(n_objects).to(dev, non_blocking=True).reshape(-1)
+        if training and self._graph_warmup > 0 and hasattr(self.optimizer, 'flat_grad') and not _lib.TIMER.enabled:
+            out = self.__graph_step(images, sem, ins, nobj, q_den, clip_grad_norm, criterion_type)
             if out is not None:
                 return out
-        return self.__eager_step(images, sem_seg_annotations, ins_seg_annotations, n_objects, clip_grad_norm, criterion_type, training)
-
-    def __eager_step(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, clip_grad_norm, criterion_type, training):
-        dev = self.device
-        ins = ins_seg_annotations.to(dev, non_blocking=True)
-        out_metrics = self.__fwd_bwd(images, sem_seg_annotations, ins, n_objects, criterion_type, training, self.__q_denominator(ins))
+        out_metrics = self.__fwd_bwd(images, sem, ins, nobj, criterion_type, training, q_den)
         if training:
             self.__update(clip_grad_norm)
         return out_metrics
 
-    def __fwd_bwd(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, criterion_type, training, q_den):
-        """Forward, losses and (training) zero_grad + backward; returns the metrics dict of model.py:242-269."""
+    def __fwd_bwd(self, images, sem_map, ins, nobj, criterion_type, training, q_den):
+        """Forward, losses and (training) zero_grad + backward on COMPACT device targets; returns the metrics dict of
+        model.py:242-269."""
         self.model.train(training)
-        dev = self.device
-        images = images.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
-        sem = sem_seg_annotations.to(dev, non_blocking=True)
-        ins = ins_seg_annotations.to(dev, non_blocking=True)
-        nobj = torch.as_tensor(n_objects).to(dev, non_blocking=True).reshape(-1)
+        images = images.contiguous(memory_format=torch.channels_last)
         out_metrics = dict()
         with torch.set_grad_enabled(training):
             sem_seg_predictions, ins_seg_predictions = self.model(training, images)
@@ -227,15 +234,14 @@ class Model(object):
                                                                  q_denominator=q_den)
                 cost = cost + ins_cost
                 out_metrics['INS Cost'] = ins_cost.detach()
-            if criterion_type in ['CE', 'Multi']:
-                _, sem_idx = sem.max(1)
-                ce_cost = self.criterion_ce(sem_seg_predictions, sem_idx)
-                cost = cost + ce_cost
-                out_metrics['CE Cost'] = ce_cost.detach()
-            if criterion_type in ['Dice', 'Multi']:
-                dice_cost = self.criterion_dice(sem_seg_predictions, sem, time=1)
-                cost = cost + dice_cost
-                out_metrics['Dice Cost'] = dice_cost.detach()
+            if criterion_type in ['CE', 'Dice', 'Multi']:
+                ce_cost, dice_cost = self.criterion_seg(sem_seg_predictions, sem_map, time=1)   # model.py:255-269
+                if criterion_type in ['CE', 'Multi']:
+                    cost = cost + ce_cost
+                    out_metrics['CE Cost'] = ce_cost.detach()
+                if criterion_type in ['Dice', 'Multi']:
+                    cost = cost + dice_cost
+                    out_metrics['Dice Cost'] = dice_cost.detach()
             out_metrics['Cost'] = cost.detach()
         if training:
             if hasattr(self.optimizer, 'flat_grad'):
@@ -301,6 +307,9 @@ class Model(object):
         return history
 
     def __run_epoch(self, loader, clip_grad_norm, mode):
+        """Mean metrics of one pass over `loader`.  Data parallel: every rank sees its own shard, so the sums are
+        all-reduced -- ReduceLROnPlateau (whose learning rate is a per-rank kernel argument) and the best-checkpoint
+        test then see the SAME validation cost on every rank and the replicas cannot drift apart."""
         from .data import CudaPrefetcher
         sums, n = {}, 0
         for images, sem, ins, nobj in CudaPrefetcher(loader, self.device):
@@ -308,7 +317,15 @@ class Model(object):
             for k, v in m.items():
                 sums[k] = sums.get(k, 0.0) + v
             n += 1
-        return {k: float(v) / max(n, 1) for k, v in sums.items()}
+        keys = sorted(sums)
+        if self.distributed:
+            packed = torch.stack([torch.as_tensor(sums[k], dtype=torch.float64, device=self.device).reshape(()) for k in keys]
+                                 + [torch.tensor(float(n), dtype=torch.float64, device=self.device)])
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            packed = packed.cpu()
+            n = int(packed[-1].item())
+            sums = {k: packed[i] for i, k in enumerate(keys)}
+        return {k: float(sums[k]) / max(n, 1) for k in keys}
 
     # ------------------------------------------------------------------ predict (model.py:466-499)
     @torch.no_grad()

@@ -103,11 +103,15 @@ class Prediction(object):
         dev = self.model.device
         q = queue.Queue(maxsize=max(1, int(prefetch)))
 
+        failure = []
+
         def producer():
             try:
                 for raw in raw_images:
                     image, h, w = self.image_to_tensor(raw)
                     q.put((image.unsqueeze(0).pin_memory(), h, w))
+            except BaseException as e:      # re-raised in the consumer: a failed load must not truncate the run silently
+                failure.append(e)
             finally:
                 q.put(None)
 
@@ -151,6 +155,8 @@ class Prediction(object):
             if cur is None:
                 break
             pending = cur
+        if failure:
+            raise failure[0]
 
     def predict(self, image_path):
         raw_image = np.array(Image.open(image_path).convert('RGB'))
