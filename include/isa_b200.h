@@ -191,20 +191,6 @@ int isa_gru_scan_bwd(const float* dout, const float* out, const float* stash, co
                      int inner, long long outer_tok_stride, long long inner_tok_stride, long long t_tok_stride,
                      float* dgx, float* dghn, isa_stream_t stream);
 
-/* ------------------------------------------------------------------ fp32 -> 3 x bf16 operand split
- * The ReNet projections (x W_ih^T, dG W_ih, dG^T [x | h_prev | 1]) are plain GEMMs; they run on the bf16
- * tensor pipe at fp32-level accuracy as  a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi  (one bf16 GEMM whose K
- * dimension concatenates the three pairings, fp32 accumulate).  This writes the three parts of a row-major
- * fp32 matrix src [rows][cols] (row stride src_ld) in one pass:
- *   order 0 (left operand): (hi, hi, lo);  order 1 (right operand): (hi, lo, hi);
- *   part q of element (r, c) -> dst[q * part_stride + r * dst_ld + c]   (bf16).
- * pos_step != 0: read row r + shift instead and write zeros where the position (r / pos_div) % pos_mod
- * plus pos_step leaves [0, pos_mod): h_{t-1} of a sweep direction straight from the forward output.
- * cols, src_ld, dst_ld, part_stride: multiples of 4; src 16 B aligned. */
-int isa_split_bf16x3(const float* src, long long rows, int cols, long long src_ld, void* dst, long long dst_ld,
-                     long long part_stride, int order, long long shift, int pos_div, int pos_mod, int pos_step,
-                     isa_stream_t stream);
-
 /* ------------------------------------------------------------------ masked softmax over H*W
  * Replaces the masked spatial softmaxes of the live attention layers:
  *   /root/reference/code/lib/archs/modules/utils.py:507-512  SpatialAttentionLayer.forward
@@ -337,6 +323,24 @@ int isa_seg_losses_bwd(const float* logits, const unsigned char* class_map, cons
  * (Tensor.max(1)[1], model.py:256-257). */
 int isa_onehot_argmax(const void* target, int target_kind, int bs, int n_classes, long long HW,
                       unsigned char* class_map, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ ReNet projection GEMMs (tcgen05, fused bf16 hi/lo split)
+ * The GEMMs around the GRU scan of the ReNet contract (/root/reference/code/lib/archs/modules/README.md:225-256; nn.GRU's
+ * x W_ih^T and autograd's dG W_ih, dG^T [x | h_prev | 1]).  fp32 operands are read ONCE from global memory and split into
+ * bf16 hi + lo parts inside the kernel (a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in tensor memory,
+ * error ~2^-16 relative); nothing is transposed, concatenated or copied.  All widths multiples of 4, pointers 16 B aligned.
+ *   fwd    gx [tokens][n_out] = x [tokens][cin] w [n_out][cin]^T          (n_out = 2 directions x 3 gates x n)
+ *   dx     dx [tokens][cin]   = dg [tokens][n_out] w [n_out][cin]
+ *   wgrad  dw_ih [2][3n][cin], dw_hh [2][3n][n], db_ih [2][3n], db_hh [2][3n] from dgx [tokens][2][3n], dghn [tokens][2][n],
+ *          x [tokens][cin] and the forward output out [tokens][2][n]: h_{t-1} of direction 0 is out's row `step` tokens back,
+ *          of direction 1 `step` tokens ahead, zero outside the sweep (position = (token / pos_div) % pos_mod).  The token
+ *          dimension is split over CTAs and the partials are folded in a fixed order (deterministic). */
+int isa_renet_proj_fwd(const float* x, const float* w, long long tokens, int cin, int n_out, float* gx, isa_stream_t stream);
+int isa_renet_proj_dx(const float* dg, const float* w, long long tokens, int n_out, int cin, float* dx, isa_stream_t stream);
+size_t isa_renet_proj_wgrad_workspace_bytes(long long tokens, int cin, int n);
+int isa_renet_proj_wgrad(const float* dgx, const float* dghn, const float* x, const float* out, long long tokens, int cin, int n,
+                         long long step, int pos_div, int pos_mod, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                         void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -110,8 +110,12 @@ SIGNATURES = {
     "isa_adadelta_workspace_bytes": (c_size_t, []),
     "isa_adadelta_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_float,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
-    "isa_split_bf16x3": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_longlong,
-                                 c_longlong, c_int, c_longlong, c_int, c_int, c_int, c_void_p]),
+    # ReNet projection GEMMs
+    "isa_renet_proj_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "isa_renet_proj_dx": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "isa_renet_proj_wgrad_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
+    "isa_renet_proj_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     # fused semantic-head losses
     "isa_seg_losses_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
     "isa_seg_losses_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
@@ -131,12 +135,13 @@ KERNELS_PER_CALL = {
     "isa_disc_loss_fwd": 2, "isa_disc_loss_bwd": 2, "isa_onehot_to_labels": 1, "isa_label_fg_count": 1,
     "isa_kmeans_fit": 5, "isa_fg_compact": 3, "isa_scatter_labels_upsample": 3,
     "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 3,
-    "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1, "isa_split_bf16x3": 1,
+    "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1,
     "isa_masked_softmax_hw_fwd": 2, "isa_masked_softmax_hw_bwd": 3, "isa_row_dot": 2, "isa_row_affine": 1,
     "isa_readout_fwd": 1, "isa_readout_bwd": 1, "isa_local_attention_fwd": 1, "isa_local_attention_bwd": 2,
     "isa_bias_act_fwd": 1, "isa_bias_act_bwd": 2, "isa_add_layernorm_fwd": 1, "isa_add_layernorm_bwd": 2,
     "isa_pixel_heads_fwd": 1, "isa_pixel_heads_bwd": 1, "isa_pixel_heads_wgrad": 2,
     "isa_maxpool2x2_fwd": 1, "isa_maxpool2x2_bwd": 1, "isa_adadelta_step": 2,
+    "isa_renet_proj_fwd": 1, "isa_renet_proj_dx": 1, "isa_renet_proj_wgrad": 2,
     "isa_seg_losses_fwd": 1, "isa_seg_losses_bwd": 1, "isa_onehot_argmax": 1,
 }
 

@@ -253,6 +253,21 @@ class Model(object):
             cost.backward()
         return out_metrics
 
+    def loss_and_gradients(self, images, sem_seg_annotations, ins_seg_annotations, n_objects, criterion_type=None):
+        """One forward + backward WITHOUT the optimizer update: returns (metrics, flat fp32 gradient) -- data parallel: the
+        gradient after the all-reduce, i.e. what the update would consume.  Used to check that the data-parallel step
+        equals the single-process step on the concatenated batch (bench.py `dp_parity`, tests)."""
+        dev = self.device
+        sem, ins, q_den = self.__compact_targets(sem_seg_annotations, ins_seg_annotations)
+        nobj = torch.as_tensor(n_objects).to(dev, non_blocking=True).reshape(-1)
+        m = self.__fwd_bwd(images.to(dev, non_blocking=True), sem, ins, nobj, criterion_type or self.criterion_type, True, q_den)
+        if self.distributed:
+            self.__allreduce_gradients()
+        flat = getattr(self.optimizer, 'flat_grad', None)
+        if flat is None:
+            flat = torch.cat([p.grad.reshape(-1) for p in self.model.parameters() if p.grad is not None])
+        return m, flat
+
     def __update(self, clip_grad_norm):
         """Gradient all-reduce (data parallel), global-norm clipping and the optimizer step (model.py:271-281)."""
         if self.distributed:

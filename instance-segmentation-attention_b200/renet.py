@@ -27,29 +27,26 @@ def _geometry(B, H, W, mode):
     return B * W, H, W, H * W, 1, W  # sequences = columns, steps along h
 
 
-def _split3(src2d, dst, col0, order, shift=0, pos=(1, 1, 0)):
-    """fp32 (rows, cols) view with unit column stride -> the three bf16 parts at columns [col0, col0+cols) of
-    dst (rows, 3, ctot) (csrc/split_bf16.cu); `shift`/`pos` select a row-shifted, zero-filled read."""
-    lib = _lib.load()
-    rows, cols = src2d.shape
-    assert src2d.stride(1) == 1 and dst.dtype == torch.bfloat16 and dst.is_contiguous()
-    ctot = dst.shape[2]
-    rc = lib.isa_split_bf16x3(src2d.data_ptr(), rows, cols, src2d.stride(0), dst.data_ptr() + 2 * col0, 3 * ctot, ctot,
-                              order, shift, pos[0], pos[1], pos[2], _lib.stream_ptr(src2d.device))
-    _lib.check(rc, "isa_split_bf16x3")
-
-
 def _tensor_core_ok(*dims):
-    """The bf16x3 GEMM path needs 4-column granularity (8 B bf16 stores, 16 B fp32 loads)."""
+    """The fused-split tcgen05 GEMMs read 16-byte aligned fp32 runs: widths must be multiples of 4."""
     return all(d % 4 == 0 for d in dims)
+
+
+# useful FLOPs of the three projection GEMMs of one sweep (bench.py rooflines): 2 * M * N * K
+def bench_gemm_flops(tokens, n=100):
+    avg_cin = (256 + 200 + 200 + 200) / 4.0      # row sweep of layer 1 reads the 256-channel map, the others 2n = 200
+    return {"isa_renet_proj_fwd": 2.0 * tokens * 6 * n * avg_cin,
+            "isa_renet_proj_dx": 2.0 * tokens * 6 * n * avg_cin,
+            "isa_renet_proj_wgrad": 2.0 * tokens * (6 * n * avg_cin + 6 * n * n)}
 
 
 class _GruSweepFn(torch.autograd.Function):
     """out[tokens, 2n] = biGRU over the sequences described by `mode` of x[tokens, Cin].
 
-    Projections: x W_ih^T, dG W_ih and dG^T [x | h_prev | 1] run as bf16 tensor-core GEMMs over hi/lo-split
-    operands (fp32-level accuracy, see csrc/split_bf16.cu); shapes whose widths are not multiples of 4 take
-    the plain fp32 library GEMM."""
+    Projections: x W_ih^T, dG W_ih and [dgx | dghn]^T [x | h_prev | 1] run on tcgen05 (csrc/proj_gemm.cu): the fp32
+    operands are split into bf16 hi/lo parts inside the kernel's producer warps (fp32-level accuracy), h_prev is read
+    from the forward output with a row shift, nothing is transposed, copied or concatenated in global memory.  Shapes
+    whose widths are not multiples of 4 take the plain fp32 library GEMM."""
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, B, H, W, mode):
@@ -59,17 +56,15 @@ class _GruSweepFn(torch.autograd.Function):
         tokens = B * H * W
         x2 = x.reshape(tokens, -1)
         cin = x2.shape[1]
-        w2 = w_ih.reshape(6 * n, cin)
+        w2 = w_ih.reshape(6 * n, cin).contiguous()
         fast = _tensor_core_ok(cin, n)
         if fast:
             # input projection of both directions in one GEMM: [tokens][2][3n]; b_ih is added by the scan kernel
-            xs = torch.empty(tokens, 3, cin, device=x.device, dtype=torch.bfloat16)
-            ws = torch.empty(6 * n, 3, cin, device=x.device, dtype=torch.bfloat16)
-            _split3(x2, xs, 0, 0)
-            _split3(w2, ws, 0, 1)
-            gx = torch.mm(xs.view(tokens, 3 * cin), ws.view(6 * n, 3 * cin).t(), out_dtype=torch.float32)
+            x2 = x2.contiguous()
+            gx = torch.empty(tokens, 6 * n, device=x.device, dtype=torch.float32)
+            rc = lib.isa_renet_proj_fwd(_lib.ptr(x2), _lib.ptr(w2), tokens, cin, 6 * n, _lib.ptr(gx), _lib.stream_ptr(x.device))
+            _lib.check(rc, "isa_renet_proj_fwd")
             bias_in = b_ih.contiguous()
-            del xs
         else:
             gx = torch.addmm(b_ih.reshape(-1), x2, w2.t())
             bias_in = None
@@ -105,7 +100,7 @@ class _GruSweepFn(torch.autograd.Function):
         dg2 = dgx.view(tokens, 6 * n)
         w2 = w_ih.reshape(6 * n, cin)
         if ctx.fast:
-            return _GruSweepFn._backward_tensor_core(ctx, x2, w2, w_ih, w_hh, out, dg2, dghn.view(tokens, 2 * n))
+            return _GruSweepFn._backward_tensor_core(ctx, x2, w2.contiguous(), w_ih, w_hh, out, dgx, dghn)
         dx = dg2 @ w2 if ctx.needs_input_grad[0] else None
         dw_ih = (dg2.t() @ x2).view_as(w_ih)
         db_ih = dg2.sum(0).view(2, 3 * n)
@@ -132,57 +127,34 @@ class _GruSweepFn(torch.autograd.Function):
         return dx.view(ctx.x_shape) if dx is not None else None, dw_ih, dw_hh, db_ih, db_hh, None, None, None, None
 
     @staticmethod
-    def _backward_tensor_core(ctx, x2, w2, w_ih, w_hh, out, dg2, dghn2):
-        """Two bf16x3 GEMM groups over ONE split of the gate gradients:
-             left  L = [dgx (6n) | dghn (2n)]                      (tokens, 3, 8n)   parts (hi, hi, lo)
-             right R = [x (cin) | h_prev dir0 (n) | h_prev dir1 (n) | 1 (8)]  (tokens, 3, cin+2n+8)  parts (hi, lo, hi)
-           dx    = L_kconcat (tokens, 24n) @ W_pad (24n, cin)      (rows of W_pad under the dghn columns are zero)
-           C     = sum_parts L_p^T R_p  (8n, cin+2n+8): dW_ih, dW_hh blocks and, from the ones column, every bias gradient."""
+    def _backward_tensor_core(ctx, x2, w2, w_ih, w_hh, out, dgx, dghn):
+        """dx = dgx W_ih (one GEMM) and every weight / bias gradient from ONE product over all tokens,
+        [dgx | dghn]^T [x | h_prev(dir 0) | h_prev(dir 1) | 1], split over the tokens and folded in a fixed order."""
+        lib = _lib.load()
         B, H, W, mode, n = ctx.geom
         tokens = B * H * W
         cin = x2.shape[1]
         dev = x2.device
-        nl = 8 * n
-        nr = cin + 2 * n + 8
-        L = torch.empty(tokens, 3, nl, device=dev, dtype=torch.bfloat16)
-        _split3(dg2, L, 0, 0)
-        _split3(dghn2, L, 6 * n, 0)
+        st = _lib.stream_ptr(dev)
         dx = None
         if ctx.needs_input_grad[0]:
-            wp = torch.zeros(3, nl, cin, device=dev, dtype=torch.bfloat16)
-            # part q of W (order 1) under part q of L, rows [0, 6n) of each 8n block
-            wtmp = torch.empty(6 * n, 3, cin, device=dev, dtype=torch.bfloat16)
-            _split3(w2, wtmp, 0, 1)
-            wp[:, :6 * n] = wtmp.permute(1, 0, 2)
-            dx = torch.mm(L.view(tokens, 3 * nl), wp.view(3 * nl, cin), out_dtype=torch.float32).view(ctx.x_shape)
-        R = torch.empty(tokens, 3, nr, device=dev, dtype=torch.bfloat16)
-        _split3(x2, R, 0, 1)
-        o2 = out.view(tokens, 2 * n)
+            dx = torch.empty(tokens, cin, device=dev, dtype=torch.float32)
+            rc = lib.isa_renet_proj_dx(_lib.ptr(dgx), _lib.ptr(w2), tokens, 6 * n, cin, _lib.ptr(dx), st)
+            _lib.check(rc, "isa_renet_proj_dx")
+            dx = dx.view(ctx.x_shape)
         if mode == "hor":   # step axis = w (token stride 1), position = token % W
             step, pos_div, pos_mod = 1, 1, W
         else:               # step axis = h (token stride W), position = (token / W) % H
             step, pos_div, pos_mod = W, W, H
-        # direction 0 walks forward: h_{t-1} is the previous position; direction 1 walks backward: the next one
-        _split3(o2[:, :n], R, cin, 1, shift=-step, pos=(pos_div, pos_mod, -1))
-        _split3(o2[:, n:], R, cin + n, 1, shift=step, pos=(pos_div, pos_mod, 1))
-        ones = R[:, :, cin + 2 * n:]
-        ones.zero_()
-        ones[:, 0, 0] = 1.0
-        ones[:, 2, 0] = 1.0
-        C = (torch.mm(L[:, 0].t(), R[:, 0], out_dtype=torch.float32)
-             + torch.mm(L[:, 1].t(), R[:, 1], out_dtype=torch.float32)
-             + torch.mm(L[:, 2].t(), R[:, 2], out_dtype=torch.float32))
-        kb = cin + 2 * n   # the ones column
-        dw_ih = C[:6 * n, :cin].reshape(w_ih.shape)
-        db_ih = C[:6 * n, kb].reshape(2, 3 * n)
+        dw_ih = torch.empty_like(w_ih)
         dw_hh = torch.empty_like(w_hh)
+        db_ih = torch.empty(2, 3 * n, device=dev, dtype=torch.float32)
         db_hh = torch.empty(2, 3 * n, device=dev, dtype=torch.float32)
-        for d in range(2):
-            cols = slice(cin + d * n, cin + (d + 1) * n)
-            dw_hh[d, :2 * n] = C[3 * n * d:3 * n * d + 2 * n, cols]
-            dw_hh[d, 2 * n:] = C[6 * n + d * n:6 * n + (d + 1) * n, cols]
-            db_hh[d, :2 * n] = C[3 * n * d:3 * n * d + 2 * n, kb]
-            db_hh[d, 2 * n:] = C[6 * n + d * n:6 * n + (d + 1) * n, kb]
+        wsb = lib.isa_renet_proj_wgrad_workspace_bytes(tokens, cin, n)
+        ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+        rc = lib.isa_renet_proj_wgrad(_lib.ptr(dgx), _lib.ptr(dghn), _lib.ptr(x2), _lib.ptr(out), tokens, cin, n, step, pos_div, pos_mod,
+                                      _lib.ptr(dw_ih), _lib.ptr(dw_hh), _lib.ptr(db_ih), _lib.ptr(db_hh), _lib.ptr(ws), wsb, st)
+        _lib.check(rc, "isa_renet_proj_wgrad")
         return dx, dw_ih, dw_hh, db_ih, db_hh, None, None, None, None
 
 
