@@ -335,8 +335,13 @@ int isa_onehot_argmax(const void* target, int target_kind, int bs, int n_classes
  *          x [tokens][cin] and the forward output out [tokens][2][n]: h_{t-1} of direction 0 is out's row `step` tokens back,
  *          of direction 1 `step` tokens ahead, zero outside the sweep (position = (token / pos_div) % pos_mod).  The token
  *          dimension is split over CTAs and the partials are folded in a fixed order (deterministic). */
-int isa_renet_proj_fwd(const float* x, const float* w, long long tokens, int cin, int n_out, float* gx, isa_stream_t stream);
-int isa_renet_proj_dx(const float* dg, const float* w, long long tokens, int n_out, int cin, float* dx, isa_stream_t stream);
+/* fwd / dx: the (small, L2-resident) weight operand is packed once per call into the kernel's shared-memory tile images in
+ * `workspace` (isa_renet_proj_workspace_bytes(cin, n_out) bytes) and streamed by bulk copies; the token operand is split on the fly. */
+size_t isa_renet_proj_workspace_bytes(int cin, int n_out);
+int isa_renet_proj_fwd(const float* x, const float* w, long long tokens, int cin, int n_out, float* gx, void* workspace,
+                       size_t workspace_bytes, isa_stream_t stream);
+int isa_renet_proj_dx(const float* dg, const float* w, long long tokens, int n_out, int cin, float* dx, void* workspace,
+                      size_t workspace_bytes, isa_stream_t stream);
 size_t isa_renet_proj_wgrad_workspace_bytes(long long tokens, int cin, int n);
 int isa_renet_proj_wgrad(const float* dgx, const float* dghn, const float* x, const float* out, long long tokens, int cin, int n,
                          long long step, int pos_div, int pos_mod, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,

@@ -111,8 +111,9 @@ SIGNATURES = {
     "isa_adadelta_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_float,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     # ReNet projection GEMMs
-    "isa_renet_proj_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
-    "isa_renet_proj_dx": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "isa_renet_proj_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "isa_renet_proj_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_renet_proj_dx": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_renet_proj_wgrad_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
     "isa_renet_proj_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -141,7 +142,7 @@ KERNELS_PER_CALL = {
     "isa_bias_act_fwd": 1, "isa_bias_act_bwd": 2, "isa_add_layernorm_fwd": 1, "isa_add_layernorm_bwd": 2,
     "isa_pixel_heads_fwd": 1, "isa_pixel_heads_bwd": 1, "isa_pixel_heads_wgrad": 2,
     "isa_maxpool2x2_fwd": 1, "isa_maxpool2x2_bwd": 1, "isa_adadelta_step": 2,
-    "isa_renet_proj_fwd": 1, "isa_renet_proj_dx": 1, "isa_renet_proj_wgrad": 2,
+    "isa_renet_proj_fwd": 2, "isa_renet_proj_dx": 2, "isa_renet_proj_wgrad": 2,
     "isa_seg_losses_fwd": 1, "isa_seg_losses_bwd": 1, "isa_onehot_argmax": 1,
 }
 

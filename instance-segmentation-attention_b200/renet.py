@@ -62,7 +62,10 @@ class _GruSweepFn(torch.autograd.Function):
             # input projection of both directions in one GEMM: [tokens][2][3n]; b_ih is added by the scan kernel
             x2 = x2.contiguous()
             gx = torch.empty(tokens, 6 * n, device=x.device, dtype=torch.float32)
-            rc = lib.isa_renet_proj_fwd(_lib.ptr(x2), _lib.ptr(w2), tokens, cin, 6 * n, _lib.ptr(gx), _lib.stream_ptr(x.device))
+            wsb = lib.isa_renet_proj_workspace_bytes(cin, 6 * n)
+            wpk = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+            rc = lib.isa_renet_proj_fwd(_lib.ptr(x2), _lib.ptr(w2), tokens, cin, 6 * n, _lib.ptr(gx), _lib.ptr(wpk), wsb,
+                                        _lib.stream_ptr(x.device))
             _lib.check(rc, "isa_renet_proj_fwd")
             bias_in = b_ih.contiguous()
         else:
@@ -139,7 +142,9 @@ class _GruSweepFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(tokens, cin, device=dev, dtype=torch.float32)
-            rc = lib.isa_renet_proj_dx(_lib.ptr(dgx), _lib.ptr(w2), tokens, 6 * n, cin, _lib.ptr(dx), st)
+            wsb = lib.isa_renet_proj_workspace_bytes(cin, 6 * n)
+            wpk = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            rc = lib.isa_renet_proj_dx(_lib.ptr(dgx), _lib.ptr(w2), tokens, 6 * n, cin, _lib.ptr(dx), _lib.ptr(wpk), wsb, st)
             _lib.check(rc, "isa_renet_proj_dx")
             dx = dx.view(ctx.x_shape)
         if mode == "hor":   # step axis = w (token stride 1), position = token % W

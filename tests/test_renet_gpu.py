@@ -91,12 +91,14 @@ def test_projection_gemms_against_float64(cuda, tokens, cin, n):
     w = torch.randn(6 * n, cin, generator=g).to(cuda)
     st = _lib.stream_ptr(cuda)
     gx = torch.empty(tokens, 6 * n, device=cuda)
-    _lib.check(lib.isa_renet_proj_fwd(_lib.ptr(x), _lib.ptr(w), tokens, cin, 6 * n, _lib.ptr(gx), st), "fwd")
+    wpb = lib.isa_renet_proj_workspace_bytes(cin, 6 * n)
+    wpk = torch.empty(wpb, device=cuda, dtype=torch.uint8)
+    _lib.check(lib.isa_renet_proj_fwd(_lib.ptr(x), _lib.ptr(w), tokens, cin, 6 * n, _lib.ptr(gx), _lib.ptr(wpk), wpb, st), "fwd")
     ref = x.double() @ w.double().t()
     assert _rel(gx, ref) < 2e-5
     dg = torch.randn(tokens, 2, 3 * n, generator=g).to(cuda)
     dx = torch.empty(tokens, cin, device=cuda)
-    _lib.check(lib.isa_renet_proj_dx(_lib.ptr(dg), _lib.ptr(w), tokens, 6 * n, cin, _lib.ptr(dx), st), "dx")
+    _lib.check(lib.isa_renet_proj_dx(_lib.ptr(dg), _lib.ptr(w), tokens, 6 * n, cin, _lib.ptr(dx), _lib.ptr(wpk), wpb, st), "dx")
     assert _rel(dx, dg.view(tokens, -1).double() @ w.double()) < 2e-5
     dghn = torch.randn(tokens, 2, n, generator=g).to(cuda)
     out = torch.randn(tokens, 2, n, generator=g).to(cuda)
