@@ -149,20 +149,26 @@ int isa_scatter_labels_upsample(const int* labels, const int* fg_index, const in
  * out [BH][Lq][dv]; lse2 [BH][Lq] = log2-sum-exp2 of the scaled scores (needed by bwd / probs; may be NULL).
  * Forward is a tcgen05 (TMEM accumulator) kernel fed by TMA bulk copies; operands are split into
  * bf16 hi+lo so products are fp32-accurate.  The L_q x L_k probabilities are produced only by
- * isa_attention_probs. */
+ * isa_attention_probs.
+ * dropout_p in [0, 1) is the reference's attention-probability dropout (nn.Dropout(attn_dropout) on the softmax output,
+ * utils.py:311,326), fused: the keep decision of element (bh, query, key) is a hash of (dropout_seed, bh, query, key), kept
+ * probabilities are scaled by 1 / (1 - p) (p quantised to 1/65536); nothing is stored, isa_attention_bwd and
+ * isa_attention_probs regenerate the same mask from the same (dropout_p, dropout_seed).  0 = no dropout (eval mode). */
 size_t isa_attention_workspace_bytes(int BH, int Lq, int Lk);
 
 int isa_attention_fwd(const float* q, const float* k, const float* v, int BH, int Lq, int Lk, int d, int dv, float temperature,
                       const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                      float dropout_p, unsigned long long dropout_seed,
                       float* out, float* lse2, void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 int isa_attention_probs(const float* q, const float* k, const float* lse2, int BH, int Lq, int Lk, int d, float temperature,
-                        const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows, float* attn,
-                        isa_stream_t stream);
+                        const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                        float dropout_p, unsigned long long dropout_seed, float* attn, isa_stream_t stream);
 
 int isa_attention_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout, const float* lse2,
                       int BH, int Lq, int Lk, int d, int dv, float temperature,
                       const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                      float dropout_p, unsigned long long dropout_seed,
                       float* dq, float* dk, float* dv_out, void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 /* ------------------------------------------------------------------ ReNet bidirectional-GRU sweeps

@@ -62,12 +62,12 @@ SIGNATURES = {
     # dense attention
     "isa_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "isa_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
-                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_int, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_attention_probs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_int, c_float, c_uint64, c_void_p, c_void_p]),
     "isa_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int, c_float,
-                                  c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_int, c_float, c_uint64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     # ReNet GRU scan
     "isa_gru_scan_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -120,6 +120,30 @@ struct MaskArgs {
   const unsigned char* full_mask;  // [n_mask_rows][Lq][Lk] or null
   int n_mask_rows;
 };
+// ---------------------------------------------------------------------------- attention-probability dropout
+// nn.Dropout(attn_dropout) on the softmax probabilities (/root/reference/code/lib/archs/modules/utils.py:311,326), fused:
+// the keep / drop decision of element (head-batch bh, query q, key k) is a pure function of (seed, bh, q, k), so the
+// forward never stores a mask and the two backward kernels regenerate it.  One 32-bit hash serves the key pair
+// (k & ~1, k | 1): 16 bits each against thr = round(p * 65536); kept probabilities are scaled by 1 / (1 - p).
+struct DropArgs {
+  uint32_t seed;      // already mixed with the call's seed / offset
+  uint32_t thr;       // 0 = no dropout
+  float scale;        // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {          // "lowbias32" integer finaliser
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_row_key(const DropArgs& d, int bh, int q) {
+  return hash32(d.seed + (uint32_t)bh * 0x9E3779B1u + (uint32_t)q * 0x85EBCA77u);
+}
+// 16-bit lottery numbers of keys 2*kpair (low half) and 2*kpair + 1 (high half) for the query behind `rowkey`
+__device__ __forceinline__ uint32_t drop_pair(uint32_t rowkey, int kpair) { return hash32(rowkey + (uint32_t)kpair * 0xC2B2AE3Du); }
+__device__ __forceinline__ bool drop_one(const DropArgs& d, uint32_t rowkey, int k) {
+  const uint32_t h = drop_pair(rowkey, k >> 1);
+  return ((k & 1) ? (h >> 16) : (h & 0xffffu)) < d.thr;
+}
+
 // 128-bit mask of the keys [key0, key0+128) that are masked for query `row` (bit set = masked), incl. keys >= Lk
 __device__ __forceinline__ void key_bits(const MaskArgs& m, int bh, int row, int Lq, int Lk, int key0, uint32_t (&bits)[4]) {
 #pragma unroll
@@ -157,6 +181,7 @@ struct FwdParams {
   const unsigned char* qblk;
   const unsigned char* kvblk;
   MaskArgs mask;
+  DropArgs drop;
   float* out;    // [BH][Lq][dv]
   float* lse2;   // [BH][Lq]  log2-domain log-sum-exp of the scaled scores (for backward)
   int BH, Lq, Lk, dv, nQt, nKt;
@@ -190,8 +215,8 @@ __device__ __forceinline__ float fwd_tile_max(uint32_t t_row, const uint32_t (&b
 }
 // exp pass: P = exp2(S - m) goes back into TENSOR MEMORY as the A operand of the PV MMAs, written over the 32 S
 // columns this thread has just read: [P hi: 16 packed columns | P lo: 16 packed columns] per 32-key chunk
-template <bool MASKED>
-__device__ __forceinline__ float fwd_tile_exp(uint32_t t_row, const uint32_t (&bits)[4], float m_safe) {
+template <bool MASKED, bool DROP>
+__device__ __forceinline__ float fwd_tile_exp(uint32_t t_row, const uint32_t (&bits)[4], float m_safe, const DropArgs& drop, uint32_t rowkey, int key0) {
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -207,8 +232,13 @@ __device__ __forceinline__ float fwd_tile_exp(uint32_t t_row, const uint32_t (&b
         if ((bits[c] >> i) & 1u) p0 = 0.f;
         if ((bits[c] >> (i + 1)) & 1u) p1 = 0.f;
       }
-      l0 += p0;
+      l0 += p0;      // the softmax normaliser sums the probabilities BEFORE dropout
       l1 += p1;
+      if (DROP) {
+        const uint32_t h = drop_pair(rowkey, (key0 + c * 32 + i) >> 1);
+        p0 = ((h & 0xffffu) < drop.thr) ? 0.f : p0 * drop.scale;
+        p1 = ((h >> 16) < drop.thr) ? 0.f : p1 * drop.scale;
+      }
       split2(p0, p1, ph[i >> 1], pl[i >> 1]);
     }
     tmem_st16_issue(t_row + c * 32, ph);
@@ -307,7 +337,13 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
       const float m_new = fmaxf(m_run, m_tile);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
-      const float l_tile = masked ? fwd_tile_exp<true>(t_row, bits, m_safe) : fwd_tile_exp<false>(t_row, bits, m_safe);
+      float l_tile;
+      if (prm.drop.thr != 0u) {
+        const uint32_t rowkey = drop_row_key(prm.drop, bh, row);
+        l_tile = masked ? fwd_tile_exp<true, true>(t_row, bits, m_safe, prm.drop, rowkey, key0) : fwd_tile_exp<false, true>(t_row, bits, m_safe, prm.drop, rowkey, key0);
+      } else {
+        l_tile = masked ? fwd_tile_exp<true, false>(t_row, bits, m_safe, prm.drop, 0u, key0) : fwd_tile_exp<false, false>(t_row, bits, m_safe, prm.drop, 0u, key0);
+      }
       l_run = l_run * alpha + l_tile;
       // rescale the running output (previous PV MMAs are complete: s_full was committed after them).
       // tcgen05.ld/st are warp-collective (.sync.aligned): the branch must be warp-uniform
@@ -361,8 +397,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_kernel(const FwdParam
 // (utils.py:325-329); it is L_q x L_k per head, so it is only produced when asked for.
 __global__ void attn_probs_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ lse2,
                                   const unsigned char* __restrict__ key_mask, const unsigned char* __restrict__ full_mask, int n_mask_rows,
-                                  int Lq, int Lk, int d, float qscale, float* __restrict__ attn) {
+                                  int Lq, int Lk, int d, float qscale, DropArgs drop, float* __restrict__ attn) {
   const int bh = blockIdx.z, i = blockIdx.y;
+  const uint32_t rowkey = drop_row_key(drop, bh, i);
   const float* qi = q + ((size_t)bh * Lq + i) * d;
   const float l2 = lse2[(size_t)bh * Lq + i];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Lk; j += gridDim.x * blockDim.x) {
@@ -372,7 +409,9 @@ __global__ void attn_probs_kernel(const float* __restrict__ q, const float* __re
     bool masked = false;
     if (key_mask) masked = key_mask[(size_t)(bh % n_mask_rows) * Lk + j] != 0;
     if (!masked && full_mask) masked = full_mask[((size_t)(bh % n_mask_rows) * Lq + i) * Lk + j] != 0;
-    attn[((size_t)bh * Lq + i) * Lk + j] = masked ? 0.f : exp2f(s - l2);
+    float pr = masked ? 0.f : exp2f(s - l2);
+    if (drop.thr != 0u) pr = drop_one(drop, rowkey, j) ? 0.f : pr * drop.scale;     // what multiplied V (utils.py:326-327)
+    attn[((size_t)bh * Lq + i) * Lk + j] = pr;
   }
 }
 
@@ -427,6 +466,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const BwdPrepParams 
 struct BwdParams {
   const unsigned char* qtiles; const unsigned char* ktiles;
   MaskArgs mask;
+  DropArgs drop;
   float* dq; float* dk; float* dv;
   int BH, Lq, Lk, d, dv_dim, nQt, nKt;
   float inv_t;
@@ -462,13 +502,15 @@ struct BwdMaskCtx {           // per-thread mask state of the slow path
   bool row_masked;            // dK/dV: this key is masked for every query
   const unsigned char* fm;    // dK/dV: full mask base for this head (or null)
   int q0, Lq, Lk, own_row;
+  // dropout: dQ role: hash key of the thread's query row and the first key of its 32 columns; dK/dV role: bh (queries vary)
+  uint32_t rowkey; int k0; int bh;
 };
 
 // one thread, 32 columns: registers of S and dP -> packed bf16 hi/lo pairs of P and dA
-template <bool DKDV, bool MASKED>
+template <bool DKDV, bool MASKED, bool DROP>
 __device__ __forceinline__ void bwd_math(const uint32_t (&sr)[32], const uint32_t (&dr)[32], const float* __restrict__ st_l2, const float* __restrict__ st_dl,
-                                         float l2_row, float dl_row, const BwdMaskCtx& mc, uint32_t (&ph)[16], uint32_t (&pl)[16], uint32_t (&ah)[16],
-                                         uint32_t (&al)[16]) {
+                                         float l2_row, float dl_row, const BwdMaskCtx& mc, const DropArgs& drop, uint32_t (&ph)[16], uint32_t (&pl)[16],
+                                         uint32_t (&ah)[16], uint32_t (&al)[16]) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     float l2v[4] = {l2_row, l2_row, l2_row, l2_row}, dlv[4] = {dl_row, dl_row, dl_row, dl_row};
@@ -494,8 +536,20 @@ __device__ __forceinline__ void bwd_math(const uint32_t (&sr)[32], const uint32_
         }
         if (mk) p = 0.f;
       }
-      p4[e] = p;
-      a4[e] = p * (__uint_as_float(dr[i]) - dlv[e]);
+      // dropout: the probability that multiplied V in the forward is p * keep / (1 - p_drop); its gradient dP gets the
+      // same factor, delta = rowsum(dO * O) is unchanged
+      float dp = __uint_as_float(dr[i]);
+      float pk = p;
+      if (DROP) {
+        bool dropped;
+        if (DKDV) dropped = drop_one(drop, drop_row_key(drop, mc.bh, mc.q0 + i), mc.own_row);
+        else dropped = drop_one(drop, mc.rowkey, mc.k0 + i);
+        const float f = dropped ? 0.f : drop.scale;
+        pk = p * f;
+        dp *= f;
+      }
+      p4[e] = pk;
+      a4[e] = p * (dp - dlv[e]);
     }
     if (DKDV) {
       split2(p4[0], p4[1], ph[g * 2], pl[g * 2]);
@@ -623,6 +677,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
     float l2_row = 0.f, dl_row = 0.f;
     BwdMaskCtx mc;
     mc.bits = 0u; mc.row_masked = false; mc.fm = nullptr; mc.q0 = 0; mc.Lq = prm.Lq; mc.Lk = prm.Lk; mc.own_row = own_row;
+    mc.bh = bh; mc.k0 = 0; mc.rowkey = DKDV ? 0u : drop_row_key(prm.drop, bh, own_row);
     bool masked = false;
     if (DKDV) {
       mc.row_masked = own_row >= prm.Lk;
@@ -654,12 +709,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdParam
       tmem_ld32_wait(dr);
       const float* stats = reinterpret_cast<const float*>(sm.oth[st] + 8 * kOperandBytes);
       uint32_t ph[16], pl[16], ah[16], al[16];
+      mc.q0 = n * kTileQ + col0;
+      mc.k0 = n * kTileK + col0;
+      const bool dropping = prm.drop.thr != 0u;
       if (!masked) {
-        bwd_math<DKDV, false>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, ph, pl, ah, al);
+        if (dropping) bwd_math<DKDV, false, true>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, prm.drop, ph, pl, ah, al);
+        else bwd_math<DKDV, false, false>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, prm.drop, ph, pl, ah, al);
       } else {
         mc.bits = b ? (half ? bits[3] : bits[2]) : (half ? bits[1] : bits[0]);
-        mc.q0 = n * kTileQ + col0;
-        bwd_math<DKDV, true>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, ph, pl, ah, al);
+        if (dropping) bwd_math<DKDV, true, true>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, prm.drop, ph, pl, ah, al);
+        else bwd_math<DKDV, true, false>(sr, dr, stats + col0, stats + kTileQ + col0, l2_row, dl_row, mc, prm.drop, ph, pl, ah, al);
       }
       if (DKDV) {
         tmem_st16_issue(t_s, ph);
@@ -742,6 +801,22 @@ int check_attn(int BH, int Lq, int Lk, int d, int dv) {
   return ISA_OK;
 }
 
+// p in [0, 1): quantised to 1/65536 (the keep probability used for the 1/(1-p) scale is the quantised one, so the
+// estimator stays unbiased); seed: any 64-bit value, folded to 32 bits
+int make_drop(float p, unsigned long long seed, DropArgs* d) {
+  ISA_CHECK_ARG(p >= 0.f && p < 1.f, "attention: dropout probability %f not in [0, 1)", (double)p);
+  uint32_t thr = (uint32_t)((double)p * 65536.0 + 0.5);
+  if (thr > 65535u) thr = 65535u;
+  d->thr = thr;
+  d->scale = (float)(65536.0 / (65536.0 - (double)thr));
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull;       // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  d->seed = (uint32_t)z ^ (uint32_t)(z >> 32);
+  return ISA_OK;
+}
+
 size_t fwd_ws_bytes(int BH, int Lq, int Lk) {
   const size_t nQt = (Lq + kTileQ - 1) / kTileQ, nKt = (Lk + kTileK - 1) / kTileK;
   return isa_align_up((size_t)BH * nQt * kQTileBytes, 1024) + isa_align_up((size_t)BH * nKt * kKvTileBytes, 1024);
@@ -766,10 +841,14 @@ size_t isa_attention_workspace_bytes(int BH, int Lq, int Lk) {
 // full_mask [n_mask_rows][Lq][Lk] u8; out [BH][Lq][dv]; lse2 [BH][Lq] (may be NULL).
 int isa_attention_fwd(const float* q, const float* k, const float* v, int BH, int Lq, int Lk, int d, int dv, float temperature,
                       const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                      float dropout_p, unsigned long long dropout_seed,
                       float* out, float* lse2, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   int rc = check_attn(BH, Lq, Lk, d, dv);
   if (rc) return rc;
   ISA_CHECK_ARG(q && k && v && out && workspace, "attention_fwd: null pointer");
+  DropArgs drop;
+  rc = make_drop(dropout_p, dropout_seed, &drop);
+  if (rc) return rc;
   ISA_CHECK_ARG(temperature > 0.f, "attention_fwd: temperature must be positive");
   ISA_CHECK_ARG(!(key_mask || full_mask) || n_mask_rows > 0, "attention_fwd: n_mask_rows must be positive with a mask");
   if (workspace_bytes < isa_attention_workspace_bytes(BH, Lq, Lk)) {
@@ -791,6 +870,7 @@ int isa_attention_fwd(const float* q, const float* k, const float* v, int BH, in
   FwdParams fp;
   fp.qblk = qblk; fp.kvblk = kvblk;
   fp.mask.key_mask = key_mask; fp.mask.full_mask = full_mask; fp.mask.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
+  fp.drop = drop;
   fp.out = out; fp.lse2 = lse2; fp.BH = BH; fp.Lq = Lq; fp.Lk = Lk; fp.dv = dv; fp.nQt = nQt; fp.nKt = nKt;
   const size_t smem = sizeof(FwdSmem) + 1024;
   ISA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -801,15 +881,19 @@ int isa_attention_fwd(const float* q, const float* k, const float* v, int BH, in
 
 // attn [BH][Lq][Lk] = softmax probabilities (0 where masked) from the saved lse2.
 int isa_attention_probs(const float* q, const float* k, const float* lse2, int BH, int Lq, int Lk, int d, float temperature,
-                        const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows, float* attn, cudaStream_t stream) {
+                        const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                        float dropout_p, unsigned long long dropout_seed, float* attn, cudaStream_t stream) {
   int rc = check_attn(BH, Lq, Lk, d, 1);
+  if (rc) return rc;
+  DropArgs drop;
+  rc = make_drop(dropout_p, dropout_seed, &drop);
   if (rc) return rc;
   ISA_CHECK_ARG(q && k && lse2 && attn, "attention_probs: null pointer");
   ISA_CHECK_ARG(Lq <= 65535, "attention_probs: Lq=%d > 65535", Lq);
   int gx = (Lk + 255) / 256;
   if (gx > 64) gx = 64;
   attn_probs_kernel<<<dim3(gx, Lq, BH), 256, 0, stream>>>(q, k, lse2, key_mask, full_mask, n_mask_rows > 0 ? n_mask_rows : 1, Lq, Lk, d,
-                                                         1.4426950408889634f / temperature, attn);
+                                                         1.4426950408889634f / temperature, drop, attn);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }
@@ -818,8 +902,12 @@ int isa_attention_probs(const float* q, const float* k, const float* lse2, int B
 int isa_attention_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout, const float* lse2,
                       int BH, int Lq, int Lk, int d, int dv, float temperature,
                       const unsigned char* key_mask, const unsigned char* full_mask, int n_mask_rows,
+                      float dropout_p, unsigned long long dropout_seed,
                       float* dq, float* dk, float* dvv, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   int rc = check_attn(BH, Lq, Lk, d, dv);
+  if (rc) return rc;
+  DropArgs drop;
+  rc = make_drop(dropout_p, dropout_seed, &drop);
   if (rc) return rc;
   ISA_CHECK_ARG(q && k && v && out && dout && lse2 && dq && dk && dvv && workspace, "attention_bwd: null pointer");
   if (workspace_bytes < isa_attention_workspace_bytes(BH, Lq, Lk)) {
@@ -838,6 +926,7 @@ int isa_attention_bwd(const float* q, const float* k, const float* v, const floa
   BwdParams bp;
   bp.qtiles = qtiles; bp.ktiles = ktiles;
   bp.mask.key_mask = key_mask; bp.mask.full_mask = full_mask; bp.mask.n_mask_rows = n_mask_rows > 0 ? n_mask_rows : 1;
+  bp.drop = drop;
   bp.dq = dq; bp.dk = dk; bp.dv = dvv; bp.BH = BH; bp.Lq = Lq; bp.Lk = Lk; bp.d = d; bp.dv_dim = dv; bp.nQt = nQt; bp.nKt = nKt;
   bp.inv_t = 1.f / temperature;
   const size_t smem = sizeof(BwdSmem) + 1024;
