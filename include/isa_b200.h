@@ -291,9 +291,13 @@ int isa_pixel_heads_wgrad(const float* g0, int Co0, const float* g1, int Co1, co
  * The nn.MaxPool2d(2, 2) between the backbone's convolution stages (/root/reference/code/lib/archs/modules/vgg16.py:82-140)
  * on channels-last activations: x [N][H][W][C] -> y [N][H/2][W/2][C] (floor mode, C % 4 == 0); idx (u8, shape of y, NULL at
  * inference) records the window position 0..3 of the maximum (first maximum in row-major order, NaN wins, like PyTorch);
- * the backward scatters gy through idx into gx [N][H][W][C]. */
+ * the backward scatters gy through idx into gx [N][H][W][C].  skip_grad (optional, NULL = none): a second gradient of x --
+ * the skip connection that consumes the same activation (vgg16.py returns the stage outputs as skips) -- given as
+ * [N][H][W] pixels of C floats with a pixel stride of skip_pixel_stride floats (a channel slice of a wider NHWC gradient,
+ * e.g. torch.cat's backward) and added in the same pass: gx = scatter(gy) + skip_grad. */
 int isa_maxpool2x2_fwd(const float* x, int N, int H, int W, int C, float* y, unsigned char* idx, isa_stream_t stream);
-int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, float* gx, isa_stream_t stream);
+int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, const float* skip_grad,
+                       long long skip_pixel_stride, float* gx, isa_stream_t stream);
 
 /* ------------------------------------------------------------------ fused gradient clipping + Adadelta
  * The tail of the reference's training step (/root/reference/code/lib/model.py:271-281: clip_grad_norm_ then
@@ -352,6 +356,17 @@ size_t isa_renet_proj_wgrad_workspace_bytes(long long tokens, int cin, int n);
 int isa_renet_proj_wgrad(const float* dgx, const float* dghn, const float* x, const float* out, long long tokens, int cin, int n,
                          long long step, int pos_div, int pos_mod, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
                          void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
+/* ------------------------------------------------------------------ SBD / |DiC| of instance label images
+ * Replaces the numpy loops of /root/reference/code/evaluate.py:18-57 (calc_dice, calc_bd, calc_sbd, calc_dic):
+ * gt, pred [n_images][pixels_per_image] u8 label images (0 = background) ->
+ * out [n_images][5] f64 = {SBD, BD(gt, pred), BD(pred, gt), #objects(gt), #objects(pred)}; |DiC| = |out[3] - out[4]|.
+ * One contingency-table pass (integer atomics, exact) + a per-image reduction; every dice is the reference's ratio of
+ * integer counts in float64.  NaN where the reference returns nan (no object in the first image) or raises (none in the
+ * second).  workspace: isa_sbd_workspace_bytes(n_images). */
+size_t isa_sbd_workspace_bytes(int n_images);
+int isa_sbd(const unsigned char* gt, const unsigned char* pred, int n_images, long long pixels_per_image, double* out,
+            void* workspace, size_t workspace_bytes, isa_stream_t stream);
 
 #ifdef __cplusplus
 }

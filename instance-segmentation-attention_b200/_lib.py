@@ -106,7 +106,7 @@ SIGNATURES = {
     "isa_pixel_heads_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_longlong, c_int,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_maxpool2x2_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "isa_maxpool2x2_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "isa_maxpool2x2_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p]),
     "isa_adadelta_workspace_bytes": (c_size_t, []),
     "isa_adadelta_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_float,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -124,6 +124,9 @@ SIGNATURES = {
     "isa_seg_losses_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_onehot_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p]),
+    # evaluation
+    "isa_sbd_workspace_bytes": (c_size_t, [c_int]),
+    "isa_sbd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 
@@ -143,7 +146,7 @@ KERNELS_PER_CALL = {
     "isa_pixel_heads_fwd": 1, "isa_pixel_heads_bwd": 1, "isa_pixel_heads_wgrad": 2,
     "isa_maxpool2x2_fwd": 1, "isa_maxpool2x2_bwd": 1, "isa_adadelta_step": 2,
     "isa_renet_proj_fwd": 2, "isa_renet_proj_dx": 2, "isa_renet_proj_wgrad": 2,
-    "isa_seg_losses_fwd": 1, "isa_seg_losses_bwd": 1, "isa_onehot_argmax": 1,
+    "isa_seg_losses_fwd": 1, "isa_seg_losses_bwd": 1, "isa_onehot_argmax": 1, "isa_sbd": 2,
 }
 
 

@@ -43,9 +43,11 @@ class SkipVGG16(nn.Module):
         self.pool = MaxPool2x2()
 
     def forward(self, x):
-        s1 = self.stage1(x)
-        s2 = self.stage2(self.pool(s1))
-        x = self.stage3(self.pool(s2))
+        # each stage output feeds the next stage through the pool AND a skip connection: pool.with_skip sums the two
+        # gradients inside the pooling backward kernel
+        p1, s1 = self.pool.with_skip(self.stage1(x))
+        p2, s2 = self.pool.with_skip(self.stage2(p1))
+        x = self.stage3(p2)
         return x, s1, s2
 
 

@@ -321,9 +321,12 @@ __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __rest
   }
 }
 
+// `add` (optional): a second gradient of the pooled tensor's INPUT (the skip connection that also consumed it), read with
+// its own pixel stride (a channel slice of a wider NHWC gradient, e.g. what torch.cat's backward hands back) and summed in
+// the same pass -- autograd would otherwise materialise the scatter, copy the slice and run a separate add.
 __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __restrict__ gy, const unsigned char* __restrict__ idx,
                                                              float* __restrict__ gx, long long total4, int Ho, int Wo, int W, int C4,
-                                                             long long in_img) {
+                                                             long long in_img, const float* __restrict__ add, long long add_px) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     long long r = i / C4;
@@ -334,10 +337,15 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
     const float4 g = ld4(gy + i * 4);
     const unsigned int sel = *reinterpret_cast<const unsigned int*>(idx + i * 4);
     const unsigned int s0 = sel & 3u, s1 = (sel >> 8) & 3u, s2 = (sel >> 16) & 3u, s3 = (sel >> 24) & 3u;
+    const long long pix0 = n * ((long long)2 * Ho * W) + (long long)(2 * ho) * W + 2 * wo;   // H == 2 Ho whenever `add` is given
 #pragma unroll
     for (unsigned int q = 0; q < 4; ++q) {
       float4 o;
       o.x = s0 == q ? g.x : 0.f; o.y = s1 == q ? g.y : 0.f; o.z = s2 == q ? g.z : 0.f; o.w = s3 == q ? g.w : 0.f;
+      if (add) {
+        const float4 a = ld4(add + (pix0 + (long long)(q >> 1) * W + (q & 1)) * add_px + c4 * 4);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
       *reinterpret_cast<float4*>(gx + base + (long long)(q >> 1) * W * C4 * 4 + (q & 1) * C4 * 4) = o;
     }
   }
@@ -1330,8 +1338,12 @@ int isa_maxpool2x2_fwd(const float* x, int N, int H, int W, int C, float* y, uns
 
 // gx [N][H][W][C] = scatter of gy [N][H/2][W/2][C] to the recorded window positions (every covered element is written;
 // with odd H or W the uncovered last row / column is zeroed first).
-int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, float* gx, cudaStream_t stream) {
+int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, int W, int C, const float* skip_grad,
+                       long long skip_pixel_stride, float* gx, cudaStream_t stream) {
   ISA_CHECK_ARG(gy && idx && gx && N > 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0, "maxpool2x2_bwd: bad argument (N=%d H=%d W=%d C=%d)", N, H, W, C);
+  ISA_CHECK_ARG(!skip_grad || (!(H & 1) && !(W & 1) && skip_pixel_stride >= C && skip_pixel_stride % 4 == 0 &&
+                               (reinterpret_cast<uintptr_t>(skip_grad) & 15u) == 0),
+                "maxpool2x2_bwd: a skip gradient needs even H, W, a pixel stride >= C that is a multiple of 4 and 16-byte alignment");
   IsaDeviceInfo di;
   int rc = isa_device_info(&di);
   if (rc) return rc;
@@ -1340,7 +1352,7 @@ int isa_maxpool2x2_bwd(const float* gy, const unsigned char* idx, int N, int H, 
   const long long total4 = (long long)N * Ho * Wo * C4;
   long long grid = (total4 + 255) / 256;
   if (grid > (long long)di.num_sms * 16) grid = (long long)di.num_sms * 16;
-  maxpool2x2_bwd_kernel<<<(unsigned)grid, 256, 0, stream>>>(gy, idx, gx, total4, Ho, Wo, W, C4, (long long)H * W * C);
+  maxpool2x2_bwd_kernel<<<(unsigned)grid, 256, 0, stream>>>(gy, idx, gx, total4, Ho, Wo, W, C4, (long long)H * W * C, skip_grad, skip_pixel_stride);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }

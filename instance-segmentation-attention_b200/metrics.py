@@ -42,3 +42,29 @@ def calc_bd(ins_seg_gt, ins_seg_pred):
 
 def calc_sbd(ins_seg_gt, ins_seg_pred):
     return min(calc_bd(ins_seg_gt, ins_seg_pred), calc_bd(ins_seg_pred, ins_seg_gt))
+
+
+def sbd_device(ins_seg_gt, ins_seg_pred):
+    """SBD / best dice / object counts of uint8 label images ON THE DEVICE (csrc/eval_ops.cu): gt, pred (n, H, W) or
+    (H, W) uint8 CUDA tensors -> float64 CUDA tensor (n, 5) = [SBD, BD(gt, pred), BD(pred, gt), n_gt, n_pred]; |DiC| is
+    |n_gt - n_pred|.  Same values as calc_sbd / calc_bd above (identical ratios of integer counts in float64); NaN where
+    calc_bd returns nan or raises.  No CPU fallback."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    _lib.require_cuda(ins_seg_gt, "ins_seg_gt")
+    _lib.require_cuda(ins_seg_pred, "ins_seg_pred")
+    if ins_seg_gt.dtype != torch.uint8 or ins_seg_pred.dtype != torch.uint8:
+        raise TypeError("sbd_device: label images must be uint8")
+    gt = ins_seg_gt.contiguous()
+    pr = ins_seg_pred.contiguous()
+    if gt.shape != pr.shape or gt.dim() not in (2, 3):
+        raise ValueError("sbd_device: gt %s and pred %s must be equal-shaped (H,W) or (n,H,W)" % (tuple(gt.shape), tuple(pr.shape)))
+    n = 1 if gt.dim() == 2 else gt.shape[0]
+    P = gt.numel() // n
+    out = torch.empty(n, 5, device=gt.device, dtype=torch.float64)
+    wsb = lib.isa_sbd_workspace_bytes(n)
+    ws = torch.empty(wsb, device=gt.device, dtype=torch.uint8)
+    rc = lib.isa_sbd(_lib.ptr(gt), _lib.ptr(pr), n, P, _lib.ptr(out), _lib.ptr(ws), wsb, _lib.stream_ptr(gt.device))
+    _lib.check(rc, "isa_sbd")
+    return out

@@ -262,10 +262,22 @@ def pixel_heads(xa, xb, head0, head1=None):
     return out0, (out1 if head1 is not None else None)
 
 
+def _skip_grad_view(g, N, C, H, W):
+    """(tensor to hand to the kernel, pixel stride in floats) of a gradient that is NHWC-dense or a channel slice of a
+    wider NHWC-dense tensor (what torch.cat's backward returns); anything else is made NHWC-dense first."""
+    if g.dtype == torch.float32 and g.dim() == 4 and g.stride(1) == 1 and g.stride(3) >= C and g.stride(3) % 4 == 0 \
+            and g.stride(2) == W * g.stride(3) and g.stride(0) == H * W * g.stride(3) and g.data_ptr() % 16 == 0:
+        return g, g.stride(3)
+    g = g.contiguous(memory_format=torch.channels_last)
+    return g, C
+
+
 class _MaxPool2x2Fn(torch.autograd.Function):
+    """y = maxpool2x2(x); with `with_skip` the function also returns x itself as a second output (the skip connection), so
+    that BOTH gradients of x arrive in one backward call and are summed inside the scatter kernel."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, with_skip):
         lib = _lib.load()
         N, C, H, W = x.shape
         y = torch.empty(N, C, H // 2, W // 2, device=x.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
@@ -274,20 +286,32 @@ class _MaxPool2x2Fn(torch.autograd.Function):
         rc = lib.isa_maxpool2x2_fwd(x.data_ptr(), N, H, W, C, y.data_ptr(), _lib.ptr(idx), _lib.stream_ptr(x.device))
         _lib.check(rc, "isa_maxpool2x2_fwd")
         ctx.geom = (N, C, H, W)
+        ctx.with_skip = bool(with_skip)
         if need:
             ctx.save_for_backward(idx)
+        if with_skip:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, g_skip=None):
         lib = _lib.load()
         N, C, H, W = ctx.geom
         idx, = ctx.saved_tensors
+        gx = torch.empty(N, C, H, W, device=idx.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+        if gy is None:                       # only the skip was used downstream
+            gx.copy_(g_skip)
+            return gx, None
         gy = gy.contiguous(memory_format=torch.channels_last)
-        gx = torch.empty(N, C, H, W, device=gy.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
-        rc = lib.isa_maxpool2x2_bwd(gy.data_ptr(), idx.data_ptr(), N, H, W, C, gx.data_ptr(), _lib.stream_ptr(gy.device))
+        skip_ptr, skip_px = None, 0
+        if g_skip is not None and not ((H | W) & 1):
+            g_skip, skip_px = _skip_grad_view(g_skip, N, C, H, W)
+            skip_ptr = g_skip.data_ptr()
+        rc = lib.isa_maxpool2x2_bwd(gy.data_ptr(), idx.data_ptr(), N, H, W, C, skip_ptr, skip_px, gx.data_ptr(), _lib.stream_ptr(gy.device))
         _lib.check(rc, "isa_maxpool2x2_bwd")
-        return gx
+        if g_skip is not None and skip_ptr is None:
+            gx.add_(g_skip)
+        return gx, None
 
 
 class MaxPool2x2(nn.Module):
@@ -298,5 +322,15 @@ class MaxPool2x2(nn.Module):
         _lib.require_cuda(x, "activation")      # no CPU fallback: other layouts use the library op ON THE GPU
         if (x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2
                 and x.is_contiguous(memory_format=torch.channels_last)):
-            return _MaxPool2x2Fn.apply(x)
+            return _MaxPool2x2Fn.apply(x, False)
         return F.max_pool2d(x, 2, 2)
+
+    def with_skip(self, x):
+        """-> (pooled, skip): `skip` is x itself, routed through the pooling function so that the gradient coming back
+        through the skip connection is added inside the pooling backward kernel (one pass) instead of being copied and
+        accumulated by autograd (0.6 ms per step at batch 16)."""
+        _lib.require_cuda(x, "activation")
+        if (x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2
+                and x.is_contiguous(memory_format=torch.channels_last) and torch.is_grad_enabled() and x.requires_grad):
+            return _MaxPool2x2Fn.apply(x, True)
+        return self.forward(x), x

@@ -146,6 +146,36 @@ def test_maxpool2x2_matches_torch(cuda, N, C, H, W):
         assert torch.equal(torch.nan_to_num(MaxPool2x2()(x), nan=-7.0), torch.nan_to_num(yb, nan=-7.0))
 
 
+@pytest.mark.parametrize("N,C,H,W,wide", [(2, 64, 32, 48, 0), (2, 128, 16, 24, 100), (1, 8, 6, 10, 4), (1, 16, 7, 9, 0)])
+def test_maxpool2x2_with_skip_sums_both_gradients(cuda, N, C, H, W, wide):
+    """pool.with_skip: the pooled path and the skip path (directly, or through a channel slice of a wider concatenation like
+    torch.cat((y, skip), 1) in the decoder) both send a gradient to the same activation; the fused backward must equal
+    autograd's scatter + add."""
+    from isa_b200.pointwise import MaxPool2x2
+    torch.manual_seed(N * C + W)
+    x = torch.randn(N, C, H, W, device=cuda).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    other = torch.randn(N, max(wide, 4), H, W, device=cuda).contiguous(memory_format=torch.channels_last)
+
+    def loss(pooled, skip, wa, wb):
+        z = torch.cat((other, skip), dim=1) if wide else skip
+        return (pooled * wa).sum() + (z * wb).sum()
+
+    ya, sa = MaxPool2x2().with_skip(xa)
+    yb, sb = F.max_pool2d(xb, 2, 2), xb
+    wa = torch.randn_like(yb)
+    wb = torch.randn(N, C + (max(wide, 4) if wide else 0), H, W, device=cuda).contiguous(memory_format=torch.channels_last)
+    loss(ya, sa, wa, wb).backward()
+    loss(yb, sb, wa, wb).backward()
+    assert torch.equal(ya, yb)
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=0, atol=0)
+    # only one of the two outputs used
+    xc = x.clone().requires_grad_(True)
+    yc, sc = MaxPool2x2().with_skip(xc)
+    (sc * 2.0).sum().backward()
+    assert torch.equal(xc.grad, torch.full_like(xc, 2.0))
+
+
 def test_fused_adadelta_matches_torch(cuda):
     """clip_grad_norm_ + torch.optim.Adadelta vs the flat fused optimizer on the same parameters / gradients."""
     from isa_b200.optim import FusedAdadelta

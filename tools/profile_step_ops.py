@@ -16,7 +16,7 @@ torch.manual_seed(23)
 model = Model('CVPPP', 'ReSeg', 2, 32, use_instance_segmentation=True, n_embedding=24, device=dev)
 model.define_criterion(None, 0.5, 1.5, 2, False, 'Multi')
 model.define_optimizer(1.0, 0.001, 0.5, 25, 'Adadelta')
-img, sem, ins, labels, nobj = bench.train_batch(0, bs)
+img, sem, ins, labels, nobj = bench.train_batch(0, bs, "compact")
 b = [torch.from_numpy(a).to(dev) for a in (img, sem, ins, nobj)]
 for _ in range(4):
     model.train_step(b[0], b[1], b[2], b[3], 10.0)
