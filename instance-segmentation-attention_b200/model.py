@@ -332,15 +332,9 @@ class Model(object):
             for k, v in m.items():
                 sums[k] = sums.get(k, 0.0) + v
             n += 1
-        keys = sorted(sums)
         if self.distributed:
-            packed = torch.stack([torch.as_tensor(sums[k], dtype=torch.float64, device=self.device).reshape(()) for k in keys]
-                                 + [torch.tensor(float(n), dtype=torch.float64, device=self.device)])
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
-            packed = packed.cpu()
-            n = int(packed[-1].item())
-            sums = {k: packed[i] for i, k in enumerate(keys)}
-        return {k: float(sums[k]) / max(n, 1) for k in keys}
+            return parallel.allreduce_epoch_metrics(sums, n, self.device)
+        return {k: float(v) / max(n, 1) for k, v in sums.items()}
 
     # ------------------------------------------------------------------ predict (model.py:466-499)
     @torch.no_grad()

@@ -84,6 +84,21 @@ def global_q_denominator(local_foreground_count):
     return t
 
 
+def allreduce_epoch_metrics(sums, n, device):
+    """Per-rank metric sums + batch count of one epoch -> the SAME mean metrics on every rank.  Every rank validates on its
+    own shard, ReduceLROnPlateau's learning rate is a per-rank kernel argument of the fused optimizer and rank 0 decides
+    which checkpoint is best: fed rank-local costs, the replicas would drop the learning rate on different epochs and
+    drift apart silently.  Works on any backend (gloo in the CPU tests)."""
+    keys = sorted(sums)
+    packed = torch.stack([torch.as_tensor(sums[k], dtype=torch.float64, device=device).reshape(()) for k in keys]
+                         + [torch.tensor(float(n), dtype=torch.float64, device=device)])
+    if is_distributed():
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    packed = packed.cpu()
+    total = float(packed[-1].item())
+    return {k: float(packed[i]) / max(total, 1.0) for i, k in enumerate(keys)}
+
+
 def max_over_ranks(value, device):
     t = torch.tensor([float(value)], device=device, dtype=torch.float64)
     if is_distributed():

@@ -84,6 +84,44 @@ def test_flat_bucket_allreduce_and_global_q_denominator(tmp_path):
     assert abs(float(got["loss"]) - float(full["loss"])) < 1e-9 * max(1.0, abs(float(full["loss"])))
 
 
+def _lr_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from isa_b200 import parallel
+    parallel.init_from_env(backend="gloo")
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode='min', factor=0.5, patience=1)
+    local_sched_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(3))], lr=1.0)
+    local_sched = torch.optim.lr_scheduler.ReduceLROnPlateau(local_sched_opt, mode='min', factor=0.5, patience=1)
+    lrs, local_lrs, costs = [], [], []
+    for epoch in range(6):
+        # rank 0's shard keeps improving, rank 1's plateaus: rank-local costs would drop the lr on rank 1 only
+        local = {"Cost": (1.0 / (epoch + 1) if rank == 0 else 1.0 + 0.01 * epoch) * 3, "INS Cost": float(rank)}
+        m = parallel.allreduce_epoch_metrics(local, 3 if rank == 0 else 5, torch.device("cpu"))
+        sched.step(m["Cost"])
+        local_sched.step(local["Cost"] / 3.0)
+        lrs.append(opt.param_groups[0]["lr"])
+        local_lrs.append(local_sched_opt.param_groups[0]["lr"])
+        costs.append(m["Cost"])
+    torch.save({"lrs": lrs, "local_lrs": local_lrs, "costs": costs}, os.path.join(out_dir, "lr%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_epoch_metrics_allreduce_keeps_the_learning_rate_identical_across_ranks(tmp_path):
+    """ADVICE (round 1): ReduceLROnPlateau must see the same validation cost on every rank."""
+    world = 2
+    mp.spawn(_lr_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a = torch.load(os.path.join(str(tmp_path), "lr0.pt"))
+    b = torch.load(os.path.join(str(tmp_path), "lr1.pt"))
+    assert a["costs"] == b["costs"] and a["lrs"] == b["lrs"]
+    # sample-weighted mean over both shards: (3 * c0 + 5 * c1) / 8 with the sums as handed over
+    assert abs(a["costs"][0] - (3.0 + 3.0) / 8.0) < 1e-12
+    assert a["local_lrs"] != b["local_lrs"], "the scenario must be one where rank-local costs WOULD diverge"
+
+
 def test_shard_range_tiles_the_batch():
     from isa_b200 import parallel
     for gb in (1, 7, 16, 128):
