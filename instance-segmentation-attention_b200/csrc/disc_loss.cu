@@ -36,6 +36,7 @@ enum { TGT_LABEL_U8 = 0, TGT_DENSE_F32 = 1, TGT_DENSE_I64 = 2, TGT_DENSE_U8 = 3 
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kLabMaxCtas = 640;     // upper bound of the label-map forward's grid (2 CTAs per SM on any sm_100 part)
 
 struct DiscWs {
   // zeroed region
@@ -47,6 +48,9 @@ struct DiscWs {
   unsigned* img_cnt;  // [bs]
   unsigned* done_cnt; // [1]
   int* not_onehot;    // [1] dense target only: some pixel has several / non-unit entries -> keep the dense path
+  unsigned* tick1;    // [bs] label-map forward: CTAs of the image that have written their phase-1 partials
+  unsigned* tick2;    // [bs] ... phase-2 partials
+  unsigned* lab_bar;  // [1]  its grid barrier
   // not zeroed
   unsigned char* labels;  // [bs][P] u8 label map distilled from a dense one-hot target (255 = background)
   float* rnorm;   // [bs][K]  |mu~_k| before normalisation
@@ -55,6 +59,9 @@ struct DiscWs {
   float* reg_b;   // [bs]
   float* T;       // [bs][K][C]  bwd: dL/d(mu~_k) / count_k
   float* coef;    // [bs] cdir_b, then [1] cq
+  float* part;    // [kLabMaxCtas][K][C+1] per-CTA partial sums of the label-map forward (phase 1, then phase 2)
+  double* partq;  // [kLabMaxCtas][3]      per-CTA q-regulariser sum, foreground count, hinge sum
+  double* qb;     // [bs][2]               per-image q-regulariser sum and foreground count (fixed-order folds)
   size_t zero_bytes;
   size_t total_bytes;
 };
@@ -76,6 +83,9 @@ static DiscWs carve(void* base, int bs, int C, int K, int P) {
   w.img_cnt = (unsigned*)take(sizeof(unsigned) * bs);
   w.done_cnt = (unsigned*)take(sizeof(unsigned));
   w.not_onehot = (int*)take(sizeof(int));
+  w.tick1 = (unsigned*)take(sizeof(unsigned) * bs);
+  w.tick2 = (unsigned*)take(sizeof(unsigned) * bs);
+  w.lab_bar = (unsigned*)take(sizeof(unsigned));
   w.zero_bytes = off;
   w.labels = (unsigned char*)take((size_t)bs * P);
   w.rnorm = (float*)take(sizeof(float) * (size_t)bs * K);
@@ -84,6 +94,9 @@ static DiscWs carve(void* base, int bs, int C, int K, int P) {
   w.reg_b = (float*)take(sizeof(float) * bs);
   w.T = (float*)take(sizeof(float) * (size_t)bs * K * C);
   w.coef = (float*)take(sizeof(float) * (bs + 1));
+  w.part = (float*)take(sizeof(float) * (size_t)kLabMaxCtas * K * (C + 1));
+  w.partq = (double*)take(sizeof(double) * (size_t)kLabMaxCtas * 3);
+  w.qb = (double*)take(sizeof(double) * (size_t)bs * 2);
   w.total_bytes = off;
   return w;
 }
@@ -105,6 +118,7 @@ struct FwdParams {
   const float* q_den;  // optional override of the q-regulariser denominator (data parallel), else null
   int G;             // CTAs per image (1 => CTA loops over images, no inter-CTA barrier)
   int strips, rowsplits, rpt;
+  int lab_kernel_follows;   // dense target: skip the work when the masks turn out one-hot (the label-map kernel runs next)
 };
 
 // Reads the (up to K) mask weights of pixel p.  Returns the number of non-zero
@@ -488,9 +502,380 @@ __global__ void __launch_bounds__(kThreads, (CP <= 32) ? 2 : 1) disc_fwd_kernel(
   if (KIND == TGT_LABEL_U8) {
     disc_fwd_body<CP, TGT_LABEL_U8>(prm, prm.target);
   } else if (__ldcg(prm.ws.not_onehot) == 0) {
+    if (prm.lab_kernel_follows) return;              // one-hot after all: disc_fwd_lab_kernel (launched next) does the work
     disc_fwd_body<CP, TGT_LABEL_U8>(prm, prm.ws.labels);
   } else {
     disc_fwd_body<CP, KIND>(prm, prm.target);
+  }
+}
+
+
+// ---------------------------------------------------------------- forward, label-map targets (the hot configuration)
+// One cooperative kernel, ONE grid barrier, no float atomics (bit-reproducible run to run):
+//   phase 1   every CTA owns a contiguous pixel range of one image; a warp takes 32 consecutive pixels at a time
+//             (lane = pixel: C coalesced 128-byte loads, the pixel's channels stay in registers) and reduces each channel
+//             over the lanes that share a label with shuffles -- instance masks are spatially coherent, so most segments
+//             hold ONE label and cost 5 shuffles per channel -- into the WARP's private shared-memory accumulators;
+//             warps are folded in a fixed order into the CTA's partial, the last CTA of the image (a ticket) folds the
+//             image's partials in CTA order and finishes means, norms, N_b, distance and regulariser terms;
+//   barrier   all images' means are in L2;
+//   phase 2   the same walk (the embedding comes back from L2: 100 MB at batch 16 against 126 MB of L2): hinge, hinge sum
+//             and the per-instance hinge-gradient sums kept for backward, folded the same way; the last CTA overall
+//             combines the scalars.
+// The previous version walked pixel columns with running (label, sum) pairs and flushed the whole warp through shared
+// memory whenever ONE lane's label changed (every ~1.5 rows): 134 us at batch 16 (0.12 of the HBM roofline), 40 % of the
+// samples at its per-image barriers.  Soft / overlapping masks keep that kernel (disc_fwd_kernel above).
+struct LabParams {
+  FwdParams f;
+  int G;          // CTAs per image
+  int chunk;      // pixels per CTA (multiple of 32)
+  int priv;       // 1: per-warp accumulators (deterministic); 0: one CTA accumulator with shared atomics (K * C too large)
+};
+
+// Sum of every channel over the 32 lanes with 31 shuffles instead of 5 per channel (recursive halving: at each step a
+// lane hands half of its remaining channels to its partner and adds the partner's half of the others).  N = channel
+// count padded to a power of two (<= 32); afterwards v[0] of lane l is the total of channel (l * N) / 32.
+template <int N>
+__device__ __forceinline__ void warp_reduce_channels(float (&v)[N], int lane) {
+  static_assert(N == 8 || N == 16 || N == 32, "pad the channel count to 8, 16 or 32");
+  int o = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
+// Running per-instance sums of one warp: lane l keeps the running total of "its" channel(s) for the warp's current label in
+// registers; shared memory (the warp's private accumulators, or the CTA's with atomics) is touched only when the label
+// changes -- instance masks are spatially coherent, so that is rare.
+template <int CP>
+struct WarpRun {
+  static constexpr int N = CP <= 8 ? 8 : CP <= 16 ? 16 : 32;      // padded width of one reduction
+  static constexpr int R = CP <= 32 ? 1 : 2;                      // CP = 64: two reductions of 32 channels
+  float run[R];
+  float cnt;
+  int cur;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int r = 0; r < R; ++r) run[r] = 0.f;
+    cnt = 0.f; cur = -1;
+  }
+  __device__ __forceinline__ void flush(float* __restrict__ acc, int AW, int C, int lane, int priv, bool with_cnt) {
+    if (cur < 0) return;
+    float* row = acc + (size_t)cur * AW;
+    const int ch = (lane * N) >> 5;
+    const bool owner = ((lane * N) & 31) == 0;                    // one lane per channel
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = ch + 32 * r;
+      if (owner && c < C && run[r] != 0.f) {
+        if (priv) row[c] += run[r];
+        else atomicAdd(row + c, run[r]);
+      }
+      run[r] = 0.f;
+    }
+    if (with_cnt && lane == 0 && cnt != 0.f) {
+      if (priv) row[C] += cnt;
+      else atomicAdd(row + C, cnt);
+    }
+    cnt = 0.f; cur = -1;
+  }
+  // adds the lanes' values `val[c]` (only lanes with `in`) of label L; all 32 lanes call
+  __device__ __forceinline__ void add(const float (&val)[CP], bool in, int L, float n_in, float* __restrict__ acc, int AW, int C, int lane,
+                                      int priv, bool with_cnt) {
+    if (L != cur) { flush(acc, AW, C, lane, priv, with_cnt); cur = L; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = (in && i + 32 * r < CP) ? val[(i + 32 * r < CP) ? i + 32 * r : 0] : 0.f;
+      warp_reduce_channels<N>(v, lane);
+      run[r] += v[0];
+    }
+    cnt += n_in;
+  }
+};
+
+// sum of p[g * stride], g = 0..G-1, added in index order (deterministic) with the loads of a batch of 8 in flight together
+__device__ __forceinline__ float fold_partials(const float* __restrict__ p, size_t stride, int G) {
+  float v = 0.f;
+  int g = 0;
+  for (; g + 8 <= G; g += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = __ldcg(p + (size_t)(g + j) * stride);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += t[j];
+  }
+  for (; g < G; ++g) v += __ldcg(p + (size_t)g * stride);
+  return v;
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kThreads, 2) disc_fwd_lab_kernel(const LabParams lp) {
+  extern __shared__ float smem[];   // means [K][CP+1] | accumulators [priv ? kWarps : 1][K][C+1]
+  const FwdParams& prm = lp.f;
+  if (prm.target_kind != TGT_LABEL_U8 && __ldcg(prm.ws.not_onehot) != 0) return;   // soft masks: disc_fwd_kernel does the work
+  const unsigned char* __restrict__ labels_all = (prm.target_kind == TGT_LABEL_U8) ? (const unsigned char*)prm.target : prm.ws.labels;
+  const int C = prm.C, K = prm.K, P = prm.H * prm.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int MS = CP + 1, AW = C + 1;
+  float* __restrict__ s_mu = smem;
+  float* __restrict__ s_acc = smem + K * MS;
+  float* __restrict__ my_acc = s_acc + (lp.priv ? warp * K * AW : 0);
+  const int n_acc = (lp.priv ? kWarps : 1) * K * AW;
+  __shared__ double s_dbl[kWarps][3];
+  __shared__ int s_last;
+  const int b = blockIdx.x / lp.G, g = blockIdx.x % lp.G;
+  const int nb = min(max(__ldg(prm.n_objects + b), 0), K);
+  const float* __restrict__ emb = prm.emb + (size_t)b * C * P;
+  const unsigned char* __restrict__ lab = labels_all + (size_t)b * P;
+  // pixels are dealt to the image's CTAs in interleaved 256-pixel blocks: every CTA sees the same foreground / background
+  // mix (contiguous chunks left the CTAs of the background rows idle at the grid barrier)
+  const int p_lo = g * kWarps * 32, p_hi = P, p_step = lp.G * kWarps * 32;
+  float* __restrict__ part = prm.ws.part + (size_t)blockIdx.x * K * AW;
+  double* __restrict__ partq = prm.ws.partq + (size_t)blockIdx.x * 3;
+
+  for (int i = threadIdx.x; i < n_acc; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+
+  // ------------------------------------------------------------ phase 1: per-instance sums, counts, q-regulariser
+  double q_acc = 0.0, nfg_acc = 0.0;
+  WarpRun<CP> wr;
+  wr.init();
+  for (int p0 = p_lo + warp * 32; p0 < p_hi; p0 += p_step) {
+    const int p = p0 + lane;
+    const bool live = p < p_hi;
+    const int l = live ? (int)__ldg(lab + p) : 255;
+    float x[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) x[c] = (c < C && live) ? __ldg(emb + (size_t)c * P + p) : 0.f;
+    if (live) {
+      // q-regulariser: (|x * fg|_2 - 1)^2 for EVERY pixel (background adds 1); fg = 1 for any label below K
+      const float fg = (l < K) ? 1.f : 0.f;
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) { const float tq = x[c] * fg; ss = fmaf(tq, tq, ss); }
+      const float l2 = sqrtf(ss);
+      q_acc += (double)((l2 - 1.f) * (l2 - 1.f));
+      nfg_acc += (double)fg;
+    }
+    const bool valid = l < nb;
+    unsigned rem = __ballot_sync(0xffffffffu, valid);
+    while (rem) {
+      const int leader = __ffs(rem) - 1;
+      const int L = __shfl_sync(0xffffffffu, l, leader);
+      const bool in = valid && l == L;
+      const unsigned grp = __ballot_sync(0xffffffffu, in);
+      wr.add(x, in, L, (float)__popc(grp), my_acc, AW, C, lane, lp.priv, true);
+      rem &= ~grp;
+    }
+  }
+  wr.flush(my_acc, AW, C, lane, lp.priv, true);
+  q_acc = warp_sum_d(q_acc);
+  nfg_acc = warp_sum_d(nfg_acc);
+  if (lane == 0) { s_dbl[warp][0] = q_acc; s_dbl[warp][1] = nfg_acc; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * AW; i += kThreads) {
+    float v = s_acc[i];
+    if (lp.priv)
+      for (int w = 1; w < kWarps; ++w) v += s_acc[w * K * AW + i];     // fixed order
+    part[i] = v;
+  }
+  if (threadIdx.x == 0) {
+    double q = 0.0, nf = 0.0;
+    for (int w = 0; w < kWarps; ++w) { q += s_dbl[w][0]; nf += s_dbl[w][1]; }
+    partq[0] = q; partq[1] = nf;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(prm.ws.tick1 + b, 1u) == (unsigned)lp.G - 1u);
+  __syncthreads();
+  if (s_last) {
+    // ---- the image's last CTA: fold the partials in CTA order, then means / norms / N_b / distance / regulariser
+    __threadfence();
+    float* __restrict__ sums = prm.ws.sums + (size_t)b * K * AW;
+    const float* __restrict__ p0 = prm.ws.part + (size_t)b * lp.G * K * AW;
+    for (int i = threadIdx.x; i < K * AW; i += kThreads) sums[i] = fold_partials(p0 + i, (size_t)K * AW, lp.G);
+    if (threadIdx.x == 0) {
+      double q = 0.0, nf = 0.0;
+      for (int gg = 0; gg < lp.G; ++gg) { q += __ldcg(prm.ws.partq + ((size_t)b * lp.G + gg) * 3); nf += __ldcg(prm.ws.partq + ((size_t)b * lp.G + gg) * 3 + 1); }
+      prm.ws.qb[2 * b] = q; prm.ws.qb[2 * b + 1] = nf;
+    }
+    __syncthreads();
+    for (int k = warp; k < K; k += kWarps) {
+      float v = 0.f, v2 = 0.f, cntk = 0.f;
+      if (k < nb) {
+        cntk = sums[(size_t)k * AW + C];
+        if (lane < C) v = sums[(size_t)k * AW + lane] / cntk;
+        if (CP > 32 && lane + 32 < C) v2 = sums[(size_t)k * AW + lane + 32] / cntk;
+      }
+      float r = 1.f;
+      if (k < nb) {
+        r = sqrtf(warp_sum(v * v + v2 * v2));
+        if (prm.normalize_means) { v = v / r; v2 = v2 / r; }
+      }
+      if (lane < CP) s_mu[k * MS + lane] = v;
+      if (CP > 32 && lane + 32 < CP) s_mu[k * MS + lane + 32] = v2;
+      if (lane < C) prm.out_means[((size_t)b * K + k) * C + lane] = v;
+      if (CP > 32 && lane + 32 < C) prm.out_means[((size_t)b * K + k) * C + lane + 32] = v2;
+      if (lane == 0) prm.ws.rnorm[(size_t)b * K + k] = r;
+    }
+    __syncthreads();
+    float nsum = 0.f, dsum = 0.f, rsum = 0.f;
+    for (int k = threadIdx.x; k < nb; k += kThreads) {
+      const float ck = sums[(size_t)k * AW + C];
+      nsum += (ck == 0.f) ? nanf("") : ck;      // an instance id below n_objects without pixels: NaN like the reference
+    }
+    if (prm.w_dist != 0.f && nb > 1) {
+      for (int ij = threadIdx.x; ij < nb * nb; ij += kThreads) {
+        const int i = ij / nb, j = ij % nb;
+        if (i == j) continue;
+        float e = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float t = s_mu[i * MS + c] - s_mu[j * MS + c];
+          e = (prm.norm == 2) ? fmaf(t, t, e) : e + fabsf(t);
+        }
+        if (prm.norm == 2) e = sqrtf(e);
+        const float m = fmaxf(2.f * prm.delta_d - e, 0.f);
+        dsum = fmaf(m, m, dsum);
+      }
+    }
+    if (prm.w_reg != 0.f) {
+      for (int k = threadIdx.x; k < nb; k += kThreads) {
+        float e = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float t = s_mu[k * MS + c];
+          e = (prm.norm == 2) ? fmaf(t, t, e) : e + fabsf(t);
+        }
+        rsum += (prm.norm == 2) ? sqrtf(e) : e;
+      }
+    }
+    nsum = warp_sum(nsum); dsum = warp_sum(dsum); rsum = warp_sum(rsum);
+    __shared__ float s3[3][kWarps];
+    if (lane == 0) { s3[0][warp] = nsum; s3[1][warp] = dsum; s3[2][warp] = rsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, d = 0.f, r = 0.f;
+      for (int w = 0; w < kWarps; ++w) { a += s3[0][w]; d += s3[1][w]; r += s3[2][w]; }
+      prm.ws.Nb[b] = a;
+      prm.ws.dist_b[b] = (nb > 1) ? d / (float)(nb * (nb - 1)) : 0.f;
+      prm.ws.reg_b[b] = r / (float)nb;
+    }
+  }
+
+  // ------------------------------------------------------------ the one grid barrier: every image's means are published
+  group_barrier(prm.ws.lab_bar, gridDim.x);
+
+  for (int i = threadIdx.x; i < K * CP; i += kThreads) {
+    const int k = i / CP, c = i % CP;
+    s_mu[k * MS + c] = (c < C) ? __ldcg(prm.out_means + ((size_t)b * K + k) * C + c) : 0.f;
+  }
+  for (int i = threadIdx.x; i < n_acc; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+
+  // ------------------------------------------------------------ phase 2: hinge sum + per-instance hinge-gradient sums
+  double var_acc = 0.0;
+  wr.init();
+  for (int p0 = p_lo + warp * 32; p0 < p_hi; p0 += p_step) {
+    const int p = p0 + lane;
+    const bool live = p < p_hi;
+    const int l = live ? (int)__ldg(lab + p) : 255;
+    const bool valid = l < nb;
+    if (!__any_sync(0xffffffffu, valid)) continue;
+    float x[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) x[c] = (c < C && valid) ? __ldg(emb + (size_t)c * P + p) : 0.f;
+    float dir[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) dir[c] = 0.f;
+    float gs = 0.f;
+    if (valid) var_acc += (double)hinge_pair<CP>(x, s_mu + l * MS, C, prm.norm, prm.delta_v, 1.f, dir, gs);
+#pragma unroll
+    for (int c = 0; c < CP; ++c) dir[c] *= gs;
+    unsigned rem = __ballot_sync(0xffffffffu, valid);
+    while (rem) {
+      const int leader = __ffs(rem) - 1;
+      const int L = __shfl_sync(0xffffffffu, l, leader);
+      const bool in = valid && l == L;
+      const unsigned grp = __ballot_sync(0xffffffffu, in);
+      wr.add(dir, in, L, 0.f, my_acc, AW, C, lane, lp.priv, false);
+      rem &= ~grp;
+    }
+  }
+  wr.flush(my_acc, AW, C, lane, lp.priv, false);
+  var_acc = warp_sum_d(var_acc);
+  if (lane == 0) s_dbl[warp][2] = var_acc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * AW; i += kThreads) {
+    float v = s_acc[i];
+    if (lp.priv)
+      for (int w = 1; w < kWarps; ++w) v += s_acc[w * K * AW + i];
+    part[i] = v;
+  }
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < kWarps; ++w) v += s_dbl[w][2];
+    partq[2] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(prm.ws.tick2 + b, 1u) == (unsigned)lp.G - 1u);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float* __restrict__ gsum = prm.ws.gsum + (size_t)b * K * C;
+    const float* __restrict__ p0 = prm.ws.part + (size_t)b * lp.G * K * AW;
+    for (int i = threadIdx.x; i < K * C; i += kThreads) {
+      const int k = i / C, c = i % C;
+      gsum[i] = fold_partials(p0 + k * AW + c, (size_t)K * AW, lp.G);
+    }
+    if (threadIdx.x == 0) {
+      double v = 0.0;
+      for (int gg = 0; gg < lp.G; ++gg) v += __ldcg(prm.ws.partq + ((size_t)b * lp.G + gg) * 3 + 2);
+      prm.ws.var_sum[b] = (float)v;
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- the last image to finish combines the scalars, images in index order
+    if (threadIdx.x == 0) s_last = (atomicAdd(prm.ws.done_cnt, 1u) == (unsigned)prm.bs - 1u);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      __threadfence();
+      float v = 0.f, d = 0.f, r = 0.f;
+      double qs = 0.0, nf = 0.0;
+      for (int bb = 0; bb < prm.bs; ++bb) {
+        v += __ldcg(prm.ws.var_sum + bb) / __ldcg(prm.ws.Nb + bb);
+        d += __ldcg(prm.ws.dist_b + bb);
+        r += __ldcg(prm.ws.reg_b + bb);
+        qs += __ldcg(prm.ws.qb + 2 * bb);
+        nf += __ldcg(prm.ws.qb + 2 * bb + 1);
+      }
+      *prm.ws.qsum = qs;
+      *prm.ws.nfg = nf;                 // the backward reads the foreground count from here
+      const float inv_bs = 1.f / (float)prm.bs;
+      // discriminative.py:153-159: num = int(sum(target)); loss = sum(...)/num
+      const double qden = prm.q_den ? (double)__ldg(prm.q_den) : (double)(long long)nf;
+      const float qreg = (float)(qs / qden);
+      const float var_t = v * inv_bs;
+      const float dist_t = (prm.w_dist != 0.f) ? d * inv_bs : 0.f;
+      const float reg_t = (prm.w_reg != 0.f) ? r * inv_bs : 0.f;
+      prm.out_terms[0] = var_t; prm.out_terms[1] = dist_t; prm.out_terms[2] = reg_t; prm.out_terms[3] = qreg;
+      float loss = 0.f;
+      if (prm.w_var != 0.f) loss += prm.w_var * var_t;
+      if (prm.w_dist != 0.f) loss += prm.w_dist * dist_t;
+      if (prm.w_reg != 0.f) loss += prm.w_reg * reg_t;
+      if (prm.w_q != 0.f) loss += prm.w_q * qreg;
+      prm.out_loss[0] = loss;
+    }
   }
 }
 
@@ -801,6 +1186,62 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
   prm.out_loss = out_loss; prm.out_terms = out_terms; prm.out_means = out_means; prm.q_den = q_den;
 
   const int CP = pick_cp(C);
+  ISA_CUDA(cudaMemsetAsync(workspace, 0, prm.ws.zero_bytes, stream));
+  if (target_kind != TGT_LABEL_U8) {
+    rc = launch_onehot_to_labels(target, target_kind, bs, K, H * W, prm.ws.labels, prm.ws.not_onehot, di.num_sms, stream);
+    if (rc) return rc;
+  }
+
+  // ---- label-map forward (one grid barrier, deterministic): label maps, and dense masks that turn out one-hot
+  LabParams lp;
+  bool use_lab = !getenv("ISA_DISC_OLD_FWD");
+  size_t lab_smem = 0;
+  int lab_grid = 0;
+  if (use_lab) {
+    const size_t acc1 = sizeof(float) * (size_t)K * (C + 1), mu = sizeof(float) * (size_t)K * (CP + 1);
+    lp.priv = (mu + kWarps * acc1 <= 100 * 1024) ? 1 : 0;
+    lab_smem = mu + (lp.priv ? kWarps : 1) * acc1;
+    const void* fn = nullptr;
+    switch (CP) {
+      case 8: fn = (const void*)disc_fwd_lab_kernel<8>; break;
+      case 16: fn = (const void*)disc_fwd_lab_kernel<16>; break;
+      case 24: fn = (const void*)disc_fwd_lab_kernel<24>; break;
+      case 32: fn = (const void*)disc_fwd_lab_kernel<32>; break;
+      default: fn = (const void*)disc_fwd_lab_kernel<64>; break;
+    }
+    if (lab_smem > (size_t)di.max_smem_optin) use_lab = false;
+    int occ = 0;
+    if (use_lab) {
+      rc = allow_smem(fn, lab_smem);
+      if (rc) return rc;
+      ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, lab_smem));
+      if (occ > 2) occ = 2;
+      int nbc = di.num_sms * occ;
+      if (nbc > kLabMaxCtas) nbc = kLabMaxCtas;
+      if (occ < 1 || bs > nbc) use_lab = false;
+      else {
+        const int P = H * W;
+        int G = nbc / bs;
+        const int maxG = (P + 255) / 256;          // no point in CTAs with fewer than one warp-round of pixels
+        if (G > maxG) G = maxG;
+        if (G < 1) G = 1;
+        lp.G = G;
+        lp.chunk = (((P + G - 1) / G) + 31) / 32 * 32;
+        lab_grid = G * bs;
+      }
+    }
+    if (use_lab) {
+      lp.f = prm;
+      lp.f.G = 1; lp.f.strips = 0; lp.f.rowsplits = 0; lp.f.rpt = 0; lp.f.lab_kernel_follows = 0;
+      if (target_kind == TGT_LABEL_U8) {
+        void* args[] = {(void*)&lp};
+        ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(lab_grid), dim3(kThreads), args, lab_smem, stream));
+        return ISA_OK;
+      }
+    }
+  }
+
+  // ---- column-walk forward: soft / overlapping dense masks (and the fallback when the label-map kernel does not fit)
   const size_t smem = sizeof(float) * ((size_t)K * (CP + 1) + (size_t)K * (2 * C + 1) + (size_t)kWarps * 32 * ((C + 1) | 1));
   int occ = 0;
   switch (CP) {
@@ -821,19 +1262,28 @@ int isa_disc_loss_fwd(const float* emb, const void* target, int target_kind, con
   rowsplits = rowsplits < 1 ? 1 : (rowsplits > H ? H : rowsplits);
   prm.rpt = (H + rowsplits - 1) / rowsplits;
   prm.rowsplits = (H + prm.rpt - 1) / prm.rpt;
-
-  ISA_CUDA(cudaMemsetAsync(workspace, 0, prm.ws.zero_bytes, stream));
-  if (target_kind != TGT_LABEL_U8) {
-    rc = launch_onehot_to_labels(target, target_kind, bs, K, H * W, prm.ws.labels, prm.ws.not_onehot, di.num_sms, stream);
-    if (rc) return rc;
-  }
+  prm.lab_kernel_follows = use_lab ? 1 : 0;
   switch (CP) {
-    case 8: return launch_fwd<8>(prm, grid, smem, stream);
-    case 16: return launch_fwd<16>(prm, grid, smem, stream);
-    case 24: return launch_fwd<24>(prm, grid, smem, stream);
-    case 32: return launch_fwd<32>(prm, grid, smem, stream);
-    default: return launch_fwd<64>(prm, grid, smem, stream);
+    case 8: rc = launch_fwd<8>(prm, grid, smem, stream); break;
+    case 16: rc = launch_fwd<16>(prm, grid, smem, stream); break;
+    case 24: rc = launch_fwd<24>(prm, grid, smem, stream); break;
+    case 32: rc = launch_fwd<32>(prm, grid, smem, stream); break;
+    default: rc = launch_fwd<64>(prm, grid, smem, stream); break;
   }
+  if (rc || !use_lab) return rc;
+  {
+    const void* fn = nullptr;
+    switch (CP) {
+      case 8: fn = (const void*)disc_fwd_lab_kernel<8>; break;
+      case 16: fn = (const void*)disc_fwd_lab_kernel<16>; break;
+      case 24: fn = (const void*)disc_fwd_lab_kernel<24>; break;
+      case 32: fn = (const void*)disc_fwd_lab_kernel<32>; break;
+      default: fn = (const void*)disc_fwd_lab_kernel<64>; break;
+    }
+    void* args[] = {(void*)&lp};
+    ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(lab_grid), dim3(kThreads), args, lab_smem, stream));
+  }
+  return ISA_OK;
 }
 
 int isa_disc_loss_bwd(const float* emb, const void* target, int target_kind, const int* n_objects,
