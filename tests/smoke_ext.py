@@ -1,4 +1,4 @@
-"""Extended smoke check run by __graft_entry__.smoke() on cuda:0: one small invocation of EVERY kernel family of the hot
+"""Extended smoke check run by __graft_entry__.smoke() on cuda:0 (kept under tests/, outside the product package): one small invocation of EVERY kernel family of the hot
 path, each asserted against its oracle (oracle/ is test infrastructure: it is imported here, in the checker, never by
 the product modules).  The point is driver-visible proof: these launches are what GPUTEST.launches lists."""
 import numpy as np
