@@ -241,6 +241,11 @@ def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=150.0
                 rec["sbd_sklearn_1thread_vs_all_threads_masks"] = round(float(metrics.calc_sbd(sk_mask, KM.scatter_labels(fg, sk1))), 5)
                 skp = KM.sklearn_fit_predict(np.nextafter(X, np.float32(np.inf)).astype(np.float32), k, 0)
                 rec["sklearn_self_agreement_inputs_plus_1ulp"] = round(float(KM.partition_agreement(skp, sk)), 5)
+                # the same points with the feature columns reversed: the identical problem in exact arithmetic (every
+                # distance, mean and the k-means++ stream are unchanged), only the fp32 summation order differs
+                skr = KM.sklearn_fit_predict(np.ascontiguousarray(X[:, ::-1]), k, 0)
+                rec["sklearn_self_agreement_feature_order_reversed"] = round(float(KM.partition_agreement(skr, sk)), 5)
+                rec["sbd_sklearn_feature_order_reversed_masks"] = round(float(metrics.calc_sbd(sk_mask, KM.scatter_labels(fg, skr))), 5)
             except Exception as e:   # threadpoolctl missing: the instability evidence is skipped, the mismatch stays reported
                 rec["sklearn_self_agreement_error"] = repr(e)
         per_image.append(rec)
@@ -249,7 +254,8 @@ def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=150.0
              "images_identical_to_sklearn": int(sum(r["identical_to_sklearn"] for r in per_image)),
              "labels_identical_to_sklearn_up_to_permutation": bool(per_image) and all(r["identical_to_sklearn"] for r in per_image),
              "images_where_sklearn_disagrees_with_itself": int(sum(1 for r in per_image if min(
-                 r.get("sklearn_self_agreement_1_vs_all_threads", 1.0), r.get("sklearn_self_agreement_inputs_plus_1ulp", 1.0)) < 1.0)),
+                 r.get("sklearn_self_agreement_1_vs_all_threads", 1.0), r.get("sklearn_self_agreement_inputs_plus_1ulp", 1.0),
+                 r.get("sklearn_self_agreement_feature_order_reversed", 1.0)) < 1.0)),
              "sklearn_partition_agreement": min([r["agreement_with_sklearn"] for r in per_image]) if per_image else None,
              "per_image": per_image}
     return flags

@@ -225,22 +225,44 @@ __global__ void km_init_centers_kernel(const float* __restrict__ init, int R, in
 }
 
 // ------------------------------------------------------------------ seeding
-// squared distance of a point in registers to a vector in shared memory; both are zero padded beyond C, which is
-// exact (fma(0, 0, acc) == acc), so the loop is branch free and reads the vector with 16-byte loads
+// scikit-learn's k-means++ for float32 inputs (sklearn/cluster/_kmeans.py:180-283), decision for decision:
+//   * candidate distances through the float64 upcast of _euclidean_distances (pairwise.py): d = -2 x.y + |x|^2 + |y|^2
+//     in double (x = the candidate, y = the point), cast to fp32, clamped at 0;
+//   * candidates = searchsorted(cumsum(closest_dist_sq), uniform * current_pot): numpy's cumsum of a float32 array is a
+//     SEQUENTIAL float32 sum whose rounding drift (~1e-5 of the total) is as large as one point's share, so the picks
+//     depend on it -- reproduced exactly, in parallel, by seq_cumsum_search_cta below;
+//   * potentials (sums over points, BLAS-order dependent in scikit-learn) = the float32 rounding of the exact
+//     fixed-point sum.
+// Bit-exact with oracle/kmeans_oracle.c:isa_km_oracle_seed.
+
+// squared distance of a point in (double) registers to a candidate in shared memory; both are zero padded beyond C
+// (fma(0, 0, acc) == acc).  Products of two float32 values are exact in double, so fma == mul + add here.
 template <int CP>
-__device__ __forceinline__ float sqdist_reg_smem(const float (&x)[CP], const float* __restrict__ c, int C) {
-  float acc = 0.f;
-  (void)C;
+__device__ __forceinline__ float sqdist_upcast(const double (&x)[CP], double xx, const double* __restrict__ c, double cc) {
+  double dot = 0.0;
 #pragma unroll
-  for (int f4 = 0; f4 < CP; f4 += 4) {
-    const float4 cv = *reinterpret_cast<const float4*>(c + f4);
-    float t = __fsub_rn(x[f4], cv.x); acc = __fmaf_rn(t, t, acc);
-    t = __fsub_rn(x[f4 + 1], cv.y); acc = __fmaf_rn(t, t, acc);
-    t = __fsub_rn(x[f4 + 2], cv.z); acc = __fmaf_rn(t, t, acc);
-    t = __fsub_rn(x[f4 + 3], cv.w); acc = __fmaf_rn(t, t, acc);
+  for (int f2 = 0; f2 < CP; f2 += 2) {
+    const double2 cv = *reinterpret_cast<const double2*>(c + f2);
+    dot = __fma_rn(cv.x, x[f2], dot);
+    dot = __fma_rn(cv.y, x[f2 + 1], dot);
   }
-  return acc;
+  double d = __dmul_rn(-2.0, dot);
+  d = __dadd_rn(d, cc);
+  d = __dadd_rn(d, xx);
+  const float r = __double2float_rn(d);
+  return r > 0.f ? r : 0.f;
 }
+
+template <int CP>
+__device__ __forceinline__ double sqnorm64(const double (&x)[CP]) {
+  double s = 0.0;
+#pragma unroll
+  for (int f = 0; f < CP; ++f) s = __fma_rn(x[f], x[f], s);
+  return s;
+}
+
+// float32 value of an exact fixed-point potential: (float)ldexp((double)q, -S_d)
+__device__ __forceinline__ float pot_to_float(long long q, double ip_d) { return __double2float_rn(__dmul_rn(__ll2double_rn(q), ip_d)); }
 
 // RandomState.choice(n, p=uniform): first i with fl64((i+1)/n) > u
 __device__ inline int first_center_index(double u, int n) {
@@ -261,19 +283,197 @@ __device__ __forceinline__ long long warp_sum_q(long long q) {
   return (long long)((unsigned long long)lo + ((unsigned long long)mi << 21) + ((unsigned long long)hi << 42));
 }
 
+// ---- searchsorted on a SEQUENTIAL float32 running sum, computed in parallel and bit-exactly.
+// S_i = fl32(S_{i-1} + x_i) with x_i >= 0 looks inherently serial (62 k dependent FADDs = 0.13 ms per draw), but while S
+// stays inside one binade [2^e, 2^(e+1)) it lives on the grid u = 2^(e-23): S = m u with an integer m, and adding x moves
+// m by round-to-nearest-even(x / u) -- an INTEGER increment that depends on the past only through the parity of m (ties).
+// So a run of elements is a pair (increment if it starts on an even m, increment if it starts on an odd m), pairs
+// compose associatively, and a binade is one parallel scan.  A CTA takes 8192 elements per round (32 per thread:
+// sequential composition in registers, warp scan, cross-warp fold), keeps the prefix up to the first run in which m
+// would leave the binade (or an element is too large for the grid), replays that single run with real FADDs and goes
+// on in the new binade: ~log2(n) replays per search.  A threshold v is crossed in the first run whose final m reaches
+// v / u; that run is replayed from its exact start value to get the index.
+constexpr int kScanRun = 32;
+constexpr unsigned kScanSat = 0x40000000u;        // saturation of the run increments (anything >= 2^24 is "left the binade")
+constexpr unsigned kScanLimit = 1u << 24;
+
+struct ScanShared {
+  unsigned wsum[kSeedThreads / 32][2];
+  int wbad[kSeedThreads / 32];
+  int hit[kMaxL];
+  float hit_s[kMaxL];
+  float s, s_new;
+  int pos;
+  unsigned pending;
+};
+
+__device__ __forceinline__ unsigned scan_sat_add(unsigned a, unsigned b) {
+  const unsigned s = a + b;                        // both <= 2^30
+  return s > kScanSat ? kScanSat : s;
+}
+
+// One run of up to 32 elements from `pos` with real float32 adds (warp 0, all lanes in lockstep).
+// Crossed thresholds are written to out[] and removed from `pending`.
+__device__ __forceinline__ void scan_replay_run(const float* __restrict__ cl, int n, int pos, float& S, const double* v, int L,
+                                                unsigned& pending, int* out) {
+  const int lane = threadIdx.x & 31;
+  const int i = pos + lane;
+  const float xv = (i < n) ? __ldcg(cl + i) : 0.f;
+  const int cnt = (n - pos) < kScanRun ? (n - pos) : kScanRun;
+  for (int j = 0; j < cnt; ++j) {
+    S = __fadd_rn(S, __shfl_sync(0xffffffffu, xv, j));
+    if (pending) {
+      const double Sd = (double)S;
+      for (int t = 0; t < L; ++t)
+        if (((pending >> t) & 1u) && Sd >= v[t]) {
+          if (lane == 0) out[t] = pos + j;
+          pending &= ~(1u << t);
+        }
+    }
+  }
+}
+
+// out[t] = first i with (double)S_i >= v[t], else n - 1 (np.searchsorted(..., side='left') clipped).  Whole CTA.
+__device__ void seq_cumsum_search_cta(const float* __restrict__ cl, int n, const double* v, int L, int* out, ScanShared& sh) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kSeedThreads / 32;
+  __syncthreads();
+  if (tid == 0) { sh.s = 0.f; sh.pos = 0; sh.pending = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u); }
+  if (tid < L) out[tid] = n - 1;
+  __syncthreads();
+  while (true) {
+    const float S = sh.s;
+    const int pos = sh.pos;
+    const unsigned pending = sh.pending;
+    if (pos >= n || !pending) break;
+    if (!(S >= 0x1p-100f)) {
+      // no usable grid yet (zero / tiny running sum): one run with real adds
+      __syncthreads();                            // everyone has read the state
+      if (warp == 0) {
+        float s2 = S;
+        unsigned p2 = pending;
+        scan_replay_run(cl, n, pos, s2, v, L, p2, out);
+        if (lane == 0) { sh.s = s2; sh.pos = pos + kScanRun; sh.pending = p2; }
+      }
+      __syncthreads();
+      continue;
+    }
+    const int e = (int)((__float_as_uint(S) >> 23) & 0xffu) - 127;
+    const float scale = __uint_as_float((unsigned)(127 + 23 - e) << 23);   // 1 / u
+    const float inv = __uint_as_float((unsigned)(127 - 23 + e) << 23);     // u
+    const unsigned m = (unsigned)__fmul_rn(S, scale);                      // exact, in [2^23, 2^24)
+    if (tid < L) sh.hit[tid] = 0x7fffffff;
+    // ---- this thread's run: (increment from an even start, increment from an odd start)
+    const int i0 = pos + tid * kScanRun;
+    unsigned ie = 0, io = 0;
+    bool big = false;
+    if (i0 < n) {
+      float xv[kScanRun];
+      if (i0 + kScanRun <= n && ((reinterpret_cast<size_t>(cl + i0) & 15) == 0)) {
+#pragma unroll
+        for (int j4 = 0; j4 < kScanRun / 4; ++j4) {
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(cl + i0) + j4);
+          xv[4 * j4] = q.x; xv[4 * j4 + 1] = q.y; xv[4 * j4 + 2] = q.z; xv[4 * j4 + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kScanRun; ++j) xv[j] = (i0 + j < n) ? __ldcg(cl + i0 + j) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kScanRun; ++j) {
+        const float t = __fmul_rn(xv[j], scale);  // exact scaling (a denormal result rounds to < 0.5: increment 0 either way)
+        if (!(t < 16777216.f)) big = true;        // the element does not fit the grid of this binade
+        else {
+          const unsigned a = (unsigned)t;         // floor
+          const float f = __fsub_rn(t, (float)a); // exact
+          const unsigned base = a + (f > 0.5f ? 1u : 0u);
+          const bool tie = (f == 0.5f);
+          ie += base + (tie ? ((ie + a) & 1u) : 0u);
+          io += base + (tie ? ((1u + io + a) & 1u) : 0u);
+        }
+      }
+    }
+    // ---- inclusive warp scan of the pairs (the shuffled-in value is the EARLIER segment)
+    unsigned pe = ie, po = io;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned ae = __shfl_up_sync(0xffffffffu, pe, o), ao = __shfl_up_sync(0xffffffffu, po, o);
+      if (lane >= o) {
+        const unsigned ne = scan_sat_add(ae, (ae & 1u) ? po : pe);
+        const unsigned no = scan_sat_add(ao, ((1u + ao) & 1u) ? po : pe);
+        pe = ne; po = no;
+      }
+    }
+    if (lane == 31) { sh.wsum[warp][0] = pe; sh.wsum[warp][1] = po; }
+    __syncthreads();                                                           // A
+    unsigned mw = m;                                                           // m at the start of this warp's elements
+    for (int w2 = 0; w2 < warp; ++w2) mw = scan_sat_add(mw > kScanSat ? kScanSat : mw, (mw & 1u) ? sh.wsum[w2][1] : sh.wsum[w2][0]);
+    const unsigned m_after = scan_sat_add(mw > kScanSat ? kScanSat : mw, (mw & 1u) ? po : pe);
+    unsigned m_before = __shfl_up_sync(0xffffffffu, m_after, 1);
+    if (lane == 0) m_before = mw;
+    const bool bad = big || m_after >= kScanLimit;
+    const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) sh.wbad[warp] = badmask ? (__ffs(badmask) - 1) : 32;
+    __syncthreads();                                                           // B
+    int valid = NW * 32;
+    for (int w2 = NW - 1; w2 >= 0; --w2)
+      if (sh.wbad[w2] < 32) valid = w2 * 32 + sh.wbad[w2];
+    // ---- thresholds crossed inside the valid prefix: S_i >= v  <=>  m_i >= v / u
+    for (int t = 0; t < L; ++t) {
+      if (!((pending >> t) & 1u)) continue;
+      const double need = __dmul_rn(v[t], (double)scale);
+      const unsigned hm = __ballot_sync(0xffffffffu, tid < valid && (double)m_after >= need);
+      if (hm && lane == 0) atomicMin(&sh.hit[t], warp * 32 + (__ffs(hm) - 1));
+    }
+    __syncthreads();                                                           // C
+    for (int t = 0; t < L; ++t)
+      if (sh.hit[t] == tid) sh.hit_s[t] = __fmul_rn((float)m_before, inv);
+    if (valid > 0 && tid == valid - 1) sh.s_new = __fmul_rn((float)m_after, inv);
+    __syncthreads();                                                           // D
+    if (warp == 0) {
+      unsigned p2 = pending;
+      for (int t = 0; t < L; ++t) {
+        const int h = sh.hit[t];
+        if (!((p2 >> t) & 1u) || h == 0x7fffffff) continue;
+        float s2 = sh.hit_s[t];
+        // replay the run that crosses v[t] from its exact start value (only threshold t is looked at)
+        const int rpos = pos + h * kScanRun;
+        const int i = rpos + lane;
+        const float xv = (i < n) ? __ldcg(cl + i) : 0.f;
+        const int cnt = (n - rpos) < kScanRun ? (n - rpos) : kScanRun;
+        for (int j = 0; j < cnt; ++j) {
+          s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, xv, j));
+          if ((double)s2 >= v[t]) {
+            if (lane == 0) out[t] = rpos + j;
+            break;
+          }
+        }
+        p2 &= ~(1u << t);
+      }
+      float s2 = valid > 0 ? sh.s_new : S;
+      int pos2 = pos + valid * kScanRun;
+      if (valid < NW * 32 && pos2 < n && p2) {
+        scan_replay_run(cl, n, pos2, s2, v, L, p2, out);   // the run that leaves the binade
+        pos2 += kScanRun;
+      }
+      if (lane == 0) { sh.s = s2; sh.pos = pos2; sh.pending = p2; }
+    }
+    __syncthreads();                                                           // E
+  }
+  __syncthreads();
+}
+
 // Greedy k-means++ for ALL restarts in one cooperative kernel.  The points are partitioned over the CTAs
-// (contiguous ranges, multiples of 32); every step of every restart is a pass over the CTA's own points:
-//   search   thresholds T = u * potential; the CTA whose range contains the crossing of the running
-//            prefix finds the candidate index (exact int64 prefix, warp scan)            -> grid barrier
-//   pass 1   potential of every (restart, trial) candidate: warp REDUX -> CTA -> one int64 atomic per
-//            (restart, trial) and CTA                                                    -> grid barrier
-//   pass 2   best trial per restart (argmin, first wins), closest = min(closest, d(best)),
-//            per-CTA totals for the next search                                          -> grid barrier
-// r1a's version ran one 512-thread CTA per restart (35 of 148 SMs busy, 9.5 ms); here every SM works on
-// every restart and the embedding tile of a CTA stays in L1 between passes.
+// (contiguous ranges, multiples of 32); every step of every restart is
+//   search   CTA (r mod G) finds the L candidates of restart r: thresholds u * float32(potential) against the
+//            sequential float32 running sum of closest[] (seq_cumsum_search_cta)                 -> grid barrier
+//   pass 1   potential of every (restart, trial) candidate over the CTA's own points: warp REDUX -> CTA -> one
+//            int64 atomic per (restart, trial) and CTA                                           -> grid barrier
+//   pass 2   best trial per restart (lowest float32 potential, first wins), closest = min(closest, d(best)),
+//            per-CTA totals for the next potential                                               -> grid barrier
 // RES (tile-resident): the launch has at least ceil(ld / 256) CTAs, so every CTA owns at most 256 points = one point
-// per thread: the point's features stay in REGISTERS and closest[] of all restarts in shared memory for the whole
-// seeding, and warps without points skip the passes.
+// per thread: the point's features stay in REGISTERS (as doubles) and closest[] of all restarts in shared memory for
+// the whole seeding (a copy goes to global memory for the searches), and warps without points skip the passes.
 template <int CP, bool RES>
 __global__ void __launch_bounds__(kSeedThreads, 2)
 km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, int R, const double* __restrict__ uniforms, KmWs ws) {
@@ -288,15 +488,15 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   const int per = 1 + (k - 1) * L;
   const int RL = R * L;
 
-  float* s_cand = reinterpret_cast<float*>(seed_smem);                         // [R][L][CP]
-  long long* s_pot = reinterpret_cast<long long*>(s_cand + (size_t)RL * CP);   // [NW][R*L]  (8 B aligned: RL*CP*4 is a multiple of 8)
-  long long* s_base = s_pot + (size_t)NW * RL;                                 // [R] exclusive prefix of this CTA
-  long long* s_total = s_base + R;                                             // [R] potential of restart r
-  long long* s_mytot = s_total + R;                                            // [R] this CTA's share
-  long long* s_Tq = s_mytot + R;                                               // [R*L] thresholds of the current step
-  int* s_best = reinterpret_cast<int*>(s_Tq + RL);                             // [R]
+  double* s_cand = reinterpret_cast<double*>(seed_smem);                       // [R][L][CP] candidate rows (double)
+  double* s_cc = s_cand + (size_t)RL * CP;                                     // [R*L] their squared norms
+  double* s_v = s_cc + RL;                                                     // [kMaxL] thresholds of the restart being searched
+  long long* s_pot = reinterpret_cast<long long*>(s_v + kMaxL);                // [NW][R*L]
+  int* s_best = reinterpret_cast<int*>(s_pot + (size_t)NW * RL);               // [R]
   int* s_cidx = s_best + R;                                                    // [R*L] candidate indices of the current step
-  float* s_cl = reinterpret_cast<float*>(s_cidx + RL + (RL & 1));              // RES: [R][kSeedThreads] closest[] of this CTA's points
+  float* s_cl = reinterpret_cast<float*>(s_cidx + RL);                         // RES: [R][kSeedThreads] closest[] of this CTA's points
+  __shared__ ScanShared s_scan;
+  __shared__ long long s_tot;
 
   const int PT = ((n + G - 1) / G + 31) / 32 * 32;      // points per CTA
   const int p_lo = min(n, b * PT), p_hi = min(n, p_lo + PT);
@@ -311,26 +511,36 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   __syncthreads();
   for (int idx = threadIdx.x; idx < R * CP; idx += kSeedThreads) {
     const int r = idx / CP, f = idx % CP;
-    s_cand[(size_t)r * L * CP + f] = (f < C) ? Xc[(size_t)f * ld + s_best[r]] : 0.f;
+    s_cand[(size_t)r * L * CP + f] = (f < C) ? (double)Xc[(size_t)f * ld + s_best[r]] : 0.0;
   }
   for (int idx = threadIdx.x; idx < NW * RL; idx += kSeedThreads) s_pot[idx] = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += kSeedThreads) {
+    const double* c = s_cand + (size_t)r * L * CP;
+    double s = 0.0;
+    for (int f = 0; f < CP; ++f) s = __fma_rn(c[f], c[f], s);
+    s_cc[r * L] = s;
+  }
   __syncthreads();
   // RES: this thread's point for the whole kernel
   const int my_i = p_lo + threadIdx.x;
   const bool my_ok = my_i < p_hi;
   const bool warp_ok = (p_lo + warp * 32) < p_hi;       // warps without points skip the passes
-  float xr[CP];
+  double xr[CP];
+  double xxr = 0.0;
   if (RES) {
 #pragma unroll
-    for (int f = 0; f < CP; ++f) xr[f] = (my_ok && f < C) ? Xc[(size_t)f * ld + my_i] : 0.f;
+    for (int f = 0; f < CP; ++f) xr[f] = (my_ok && f < C) ? (double)Xc[(size_t)f * ld + my_i] : 0.0;
+    xxr = sqnorm64<CP>(xr);
   }
   if (RES) {
     if (warp_ok)
       for (int r = 0; r < R; ++r) {
         long long q = 0;
         if (my_ok) {
-          const float d = sqdist_reg_smem<CP>(xr, s_cand + (size_t)r * L * CP, C);
+          const float d = sqdist_upcast<CP>(xr, xxr, s_cand + (size_t)r * L * CP, s_cc[r * L]);
           s_cl[r * kSeedThreads + threadIdx.x] = d;
+          ws.closest[(size_t)r * ld + my_i] = d;
           q = to_fixed(d, sc.p_d);
         }
         q = warp_sum_q(q);
@@ -340,13 +550,14 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
     const int i = i0 + threadIdx.x;
     const bool ok = i < p_hi;
-    float x[CP];
+    double x[CP];
 #pragma unroll
-    for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+    for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? (double)Xc[(size_t)f * ld + i] : 0.0;
+    const double xx = sqnorm64<CP>(x);
     for (int r = 0; r < R; ++r) {
       long long q = 0;
       if (ok) {
-        const float d = sqdist_reg_smem<CP>(x, s_cand + (size_t)r * L * CP, C);
+        const float d = sqdist_upcast<CP>(x, xx, s_cand + (size_t)r * L * CP, s_cc[r * L]);
         ws.closest[(size_t)r * ld + i] = d;
         q = to_fixed(d, sc.p_d);
       }
@@ -360,66 +571,26 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
     for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + r * L];
     ws.seed_tot[(size_t)r * kSeedMaxCtas + b] = t;
   }
-  if (b == 0)
-    for (int idx = threadIdx.x; idx < RL; idx += kSeedThreads) ws.seed_cand[idx] = n - 1;   // np.clip(candidate_ids, None, n-1)
   grid_barrier(ws.seed_barrier, epoch);
 
   for (int c = 1; c < k; ++c) {
-    // ---- search: prefix of the per-CTA totals, then the crossing inside this CTA's range.
-    //      All global reads of a thread are independent and issued together (one L2 round trip per phase).
-    for (int r = warp; r < R; r += NW) {
-      long long v[kSeedMaxCtas / 32];
-#pragma unroll
-      for (int j = 0; j < kSeedMaxCtas / 32; ++j) {
-        const int g = lane + 32 * j;
-        v[j] = (g < G) ? __ldcg(ws.seed_tot + (size_t)r * kSeedMaxCtas + g) : 0;
+    // ---- search: CTA (r mod G) draws the L candidates of restart r
+    for (int r = b; r < R; r += G) {
+      __syncthreads();
+      if (warp == 0) {
+        long long tot = 0;
+        for (int g = lane; g < G; g += 32) tot += __ldcg(ws.seed_tot + (size_t)r * kSeedMaxCtas + g);
+        tot = warp_sum_ll(tot);
+        if (lane == 0) s_tot = tot;
       }
-      long long pre = 0, tot = 0, mine = 0;
-#pragma unroll
-      for (int j = 0; j < kSeedMaxCtas / 32; ++j) {
-        const int g = lane + 32 * j;
-        tot += v[j];
-        if (g < b) pre += v[j];
-        if (g == b) mine = v[j];
+      __syncthreads();
+      if (threadIdx.x < L) {
+        // rand_vals = random_state.uniform(size=L) * current_pot: float64 * float32 -> float64
+        const float pot = pot_to_float(s_tot, sc.ip_d);
+        s_v[threadIdx.x] = __dmul_rn(uniforms[(size_t)r * per + 1 + (c - 1) * L + threadIdx.x], (double)pot);
       }
-      pre = warp_sum_ll(pre);
-      tot = warp_sum_ll(tot);
-      mine = warp_sum_ll(mine);
-      if (lane == 0) { s_base[r] = pre; s_total[r] = tot; s_mytot[r] = mine; }
-    }
-    __syncthreads();
-    // thresholds of every (restart, trial): T = u * potential, rounded up to the fixed-point grid
-    for (int pair = threadIdx.x; pair < RL; pair += kSeedThreads) {
-      const int r = pair / L, t = pair % L;
-      const double T = __dmul_rn(uniforms[(size_t)r * per + 1 + (c - 1) * L + t], __ll2double_rn(s_total[r]));
-      s_Tq[pair] = __double2ll_ru(T);
-    }
-    __syncthreads();
-    for (int pair = warp; pair < RL; pair += NW) {
-      const int r = pair / L;
-      const long long Tq = s_Tq[pair];
-      const long long lo = s_base[r], hi = lo + s_mytot[r];
-      // first range whose inclusive prefix reaches Tq: lo < Tq <= hi, or Tq <= 0 for the first range
-      const bool mine = (p_lo < p_hi) && (hi >= Tq) && (b == 0 ? true : lo < Tq);
-      if (mine) {
-        const float* __restrict__ cl = RES ? (s_cl + r * kSeedThreads - p_lo) : (ws.closest + (size_t)r * ld);
-        long long base = lo;
-        for (int i0 = p_lo; i0 < p_hi; i0 += 32) {
-          const int i = i0 + lane;
-          long long q = (i < p_hi) ? to_fixed(cl[i], sc.p_d) : 0;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xffffffffu, q, o);
-            if (lane >= o) q += y;
-          }
-          const unsigned hit = __ballot_sync(0xffffffffu, (i < p_hi) && base + q >= Tq);
-          if (hit) {
-            if (lane == 0) ws.seed_cand[pair] = i0 + (__ffs(hit) - 1);
-            break;
-          }
-          base += __shfl_sync(0xffffffffu, q, 31);
-        }
-      }
+      __syncthreads();
+      seq_cumsum_search_cta(ws.closest + (size_t)r * ld, n, s_v, L, ws.seed_cand + (size_t)r * L, s_scan);
     }
     grid_barrier(ws.seed_barrier, epoch);
 
@@ -430,7 +601,14 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < RL * CP; idx += kSeedThreads) {
       const int pair = idx / CP, f = idx % CP;
-      s_cand[idx] = (f < C) ? Xc[(size_t)f * ld + s_cidx[pair]] : 0.f;
+      s_cand[idx] = (f < C) ? (double)Xc[(size_t)f * ld + s_cidx[pair]] : 0.0;
+    }
+    __syncthreads();
+    for (int pair = threadIdx.x; pair < RL; pair += kSeedThreads) {
+      const double* cc = s_cand + (size_t)pair * CP;
+      double s = 0.0;
+      for (int f = 0; f < CP; ++f) s = __fma_rn(cc[f], cc[f], s);
+      s_cc[pair] = s;
     }
     __syncthreads();
     if (RES) {
@@ -440,7 +618,7 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
 #pragma unroll 2
           for (int t = 0; t < L; ++t) {
             long long q = 0;
-            if (my_ok) q = to_fixed(fminf(cl, sqdist_reg_smem<CP>(xr, s_cand + (size_t)(r * L + t) * CP, C)), sc.p_d);
+            if (my_ok) q = to_fixed(fminf(cl, sqdist_upcast<CP>(xr, xxr, s_cand + (size_t)(r * L + t) * CP, s_cc[r * L + t])), sc.p_d);
             q = warp_sum_q(q);
             if (lane == 0) s_pot[(size_t)warp * RL + r * L + t] = q;   // one chunk per CTA: plain store
           }
@@ -449,14 +627,15 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
     for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
       const int i = i0 + threadIdx.x;
       const bool ok = i < p_hi;
-      float x[CP];
+      double x[CP];
 #pragma unroll
-      for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+      for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? (double)Xc[(size_t)f * ld + i] : 0.0;
+      const double xx = sqnorm64<CP>(x);
       for (int r = 0; r < R; ++r) {
         const float cl = ok ? ws.closest[(size_t)r * ld + i] : 0.f;
         for (int t = 0; t < L; ++t) {
           long long q = 0;
-          if (ok) q = to_fixed(fminf(cl, sqdist_reg_smem<CP>(x, s_cand + (size_t)(r * L + t) * CP, C)), sc.p_d);
+          if (ok) q = to_fixed(fminf(cl, sqdist_upcast<CP>(x, xx, s_cand + (size_t)(r * L + t) * CP, s_cc[r * L + t])), sc.p_d);
           q = warp_sum_q(q);
           if (lane == 0) s_pot[(size_t)warp * RL + r * L + t] += q;
         }
@@ -471,16 +650,15 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
     }
     grid_barrier(ws.seed_barrier, epoch);
 
-    // ---- best trial per restart; pass 2: closest = min(closest, d(best)), new per-CTA totals
+    // ---- best trial per restart (candidates_pot is float32; np.argmin: first lowest); pass 2: closest = min(closest,
+    //      d(best)), new per-CTA totals
     for (int r = threadIdx.x; r < R; r += kSeedThreads) {
-      long long pv[kMaxL];
-#pragma unroll
-      for (int t = 0; t < kMaxL; ++t) pv[t] = (t < L) ? __ldcg(pot_c + r * kMaxL + t) : 0;
       int best = 0;
-      long long bp = 0;
-#pragma unroll
-      for (int t = 0; t < kMaxL; ++t)
-        if (t < L && (t == 0 || pv[t] < bp)) { bp = pv[t]; best = t; }
+      float bp = 0.f;
+      for (int t = 0; t < L; ++t) {
+        const float pf = pot_to_float(__ldcg(pot_c + r * kMaxL + t), sc.ip_d);
+        if (t == 0 || pf < bp) { bp = pf; best = t; }
+      }
       s_best[r] = best;
       if (b == 0) ws.seed_idx[(size_t)r * k + c] = s_cidx[r * L + best];
     }
@@ -492,8 +670,10 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
           long long q = 0;
           if (my_ok) {
             float* cl = s_cl + r * kSeedThreads + threadIdx.x;
-            const float nd = fminf(*cl, sqdist_reg_smem<CP>(xr, s_cand + (size_t)(r * L + s_best[r]) * CP, C));
+            const int pair = r * L + s_best[r];
+            const float nd = fminf(*cl, sqdist_upcast<CP>(xr, xxr, s_cand + (size_t)pair * CP, s_cc[pair]));
             *cl = nd;
+            ws.closest[(size_t)r * ld + my_i] = nd;
             q = to_fixed(nd, sc.p_d);
           }
           q = warp_sum_q(q);
@@ -503,14 +683,16 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
     for (int i0 = p_lo; i0 < p_hi; i0 += kSeedThreads) {
       const int i = i0 + threadIdx.x;
       const bool ok = i < p_hi;
-      float x[CP];
+      double x[CP];
 #pragma unroll
-      for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? Xc[(size_t)f * ld + i] : 0.f;
+      for (int f = 0; f < CP; ++f) x[f] = (ok && f < C) ? (double)Xc[(size_t)f * ld + i] : 0.0;
+      const double xx = sqnorm64<CP>(x);
       for (int r = 0; r < R; ++r) {
         long long q = 0;
         if (ok) {
           float* cl = ws.closest + (size_t)r * ld + i;
-          const float nd = fminf(*cl, sqdist_reg_smem<CP>(x, s_cand + (size_t)(r * L + s_best[r]) * CP, C));
+          const int pair = r * L + s_best[r];
+          const float nd = fminf(*cl, sqdist_upcast<CP>(x, xx, s_cand + (size_t)pair * CP, s_cc[pair]));
           *cl = nd;
           q = to_fixed(nd, sc.p_d);
         }
@@ -524,9 +706,6 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + r * L];
       ws.seed_tot[(size_t)r * kSeedMaxCtas + b] = t;
     }
-    __syncthreads();   // every thread is past its reads of seed_cand before CTA 0 resets it
-    if (b == 0)
-      for (int idx = threadIdx.x; idx < RL; idx += kSeedThreads) ws.seed_cand[idx] = n - 1;
     grid_barrier(ws.seed_barrier, epoch);
   }
   // centres of every restart = the picked rows (CTA 0 wrote seed_idx itself)
@@ -541,7 +720,7 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
 
 size_t seed_smem_bytes(int R, int L, int CP, bool res) {
   const size_t RL = (size_t)R * L;
-  return RL * CP * 4 + (size_t)(kSeedThreads / 32) * RL * 8 + 3 * (size_t)R * 8 + RL * 8 + (size_t)R * 4 + (RL + 1) * 4 +
+  return RL * CP * 8 + RL * 8 + kMaxL * 8 + (size_t)(kSeedThreads / 32) * RL * 8 + (size_t)R * 4 + RL * 4 +
          (res ? (size_t)R * kSeedThreads * 4 : 0) + 16;
 }
 

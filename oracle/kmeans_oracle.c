@@ -17,16 +17,25 @@
  *     squared distances            (_kmeans.py:625-760, _k_means_lloyd.pyx:26-211,
  *                                   _k_means_common.pyx:13-43,167-262)
  *
- * What is pinned and what is not.  scikit-learn's own floating-point sums (BLAS sgemm/sdot,
- * sequential fp32 cumsum, per-thread partial centre sums) depend on the BLAS kernel of the
- * host CPU and on the OpenMP thread count, so its results are not bit-reproducible across
- * machines.  This oracle fixes ONE arithmetic that a GPU can reproduce bit for bit:
- *   - per-pair arithmetic in fp32 with a fixed left-to-right fmaf order;
- *   - every sum over points (column means, potentials, centre sums, inertia) in exact
- *     64-bit fixed point (order independent), scales derived from max|X|, n and C only.
- * The CUDA path must match this oracle EXACTLY (labels, n_iter, inertia, centres).  The
- * oracle itself is pinned against scikit-learn on golden vectors: labels identical up to
- * permutation when both start from the same seeds (tests/golden/kmeans_*.npz).
+ * What is pinned and what is not.  scikit-learn's own floating-point sums over points (BLAS sgemm / sgemv / sdot,
+ * per-thread partial centre sums) depend on the BLAS kernel of the host CPU and on the OpenMP thread count, so its
+ * results are not bit-reproducible across machines.  This oracle fixes ONE arithmetic that a GPU can reproduce bit
+ * for bit and that takes scikit-learn's own decisions wherever those are machine independent:
+ *   - k-means++ (_kmeans.py:180-283) exactly as scikit-learn computes it for float32 inputs: candidate distances
+ *     through the float64 upcast of _euclidean_distances (d = -2 x.y + |x|^2 + |y|^2 in double, cast to fp32,
+ *     clamped at 0: sklearn/metrics/pairwise.py _euclidean_distances_upcast), candidates drawn by searchsorted on the
+ *     SEQUENTIAL FLOAT32 cumulative sum of closest_dist_sq (numpy's cumsum of a float32 array; its rounding drift,
+ *     ~1e-5 of the total, is as large as one point's share, so an exact prefix picks different points), thresholds
+ *     u * float32(potential);
+ *   - Lloyd per-pair arithmetic in fp32 with a fixed left-to-right fmaf order (the k loop of an sgemm micro-kernel);
+ *   - every sum over points whose order scikit-learn leaves to BLAS / OpenMP (column means, potentials, centre
+ *     sums, inertia) in exact 64-bit fixed point (order independent: the correctly rounded value of the sum
+ *     scikit-learn approximates), scales derived from max|X|, n and C only.
+ * Measured on random-init network embeddings (62 k points, k = 16, tools/km_parity_probe.py): 30-34 of 35 restarts
+ * draw exactly scikit-learn's seeds (the rest differ by one neighbouring point where BLAS rounding of the potential
+ * decides), and Lloyd from identical seeds stops at scikit-learn's iteration in 7 of 8 restarts.
+ * The CUDA path must match this oracle EXACTLY (labels, seeds, n_iter, inertia, centres).  The oracle itself is
+ * pinned against scikit-learn on golden vectors (tests/golden/kmeans.npz).
  *
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off -mfma: fmaf() is a single rounding).
  */
@@ -130,44 +139,68 @@ int isa_km_oracle_prepare(float* X, int n, int C, double tol_rel, float* mean, f
   return 0;
 }
 
-/* greedy k-means++ on centred X; u = 1 + (k-1)*L uniforms of this restart. idx_out[k]. */
+/* |x|^2 of a float32 row in double: row_norms(X_chunk.astype(float64), squared=True) */
+static inline double sqnorm64(const float* a, int C) {
+  double s = 0.0;
+  for (int f = 0; f < C; ++f) s = fma((double)a[f], (double)a[f], s);
+  return s;
+}
+
+/* squared distance as sklearn's _euclidean_distances computes it for float32 inputs (pairwise.py,
+ * _euclidean_distances_upcast): d = -2 * (x . y); d += |x|^2; d += |y|^2 in float64, cast to float32, max(., 0).
+ * x = the candidate row (norm cc), y = the point (norm yy). */
+static inline float sqdist_upcast(const float* x, double cc, const float* y, double yy, int C) {
+  double dot = 0.0;
+  for (int f = 0; f < C; ++f) dot = fma((double)x[f], (double)y[f], dot);
+  double d = -2.0 * dot;
+  d += cc;
+  d += yy;
+  const float r = (float)d;
+  return r > 0.f ? r : 0.f;
+}
+
+static inline float pot_to_float(int64_t q, int S) { return (float)ldexp((double)q, -S); }
+
+/* greedy k-means++ on centred X (_kmeans.py:180-283); u = 1 + (k-1)*L uniforms of this restart; xx[n] = sqnorm64 of
+ * every row.  idx_out[k]. */
 void isa_km_oracle_seed(const float* X, int n, int C, int k, int L, const double* u, const isa_km_scales* sc,
-                        int* idx_out, float* closest /* n scratch */, float* cand_d /* n scratch */) {
+                        int* idx_out, float* closest /* n scratch */, const double* xx) {
   int c0 = first_center_index(u[0], n);
   idx_out[0] = c0;
-  int64_t pot = 0;
+  int64_t potq = 0;
   for (int i = 0; i < n; ++i) {
-    closest[i] = sqdist(X + (size_t)i * C, X + (size_t)c0 * C, C);
-    pot += to_fixed(closest[i], sc->S_d);
+    closest[i] = sqdist_upcast(X + (size_t)c0 * C, xx[c0], X + (size_t)i * C, xx[i], C);
+    potq += to_fixed(closest[i], sc->S_d);
   }
+  float pot = pot_to_float(potq, sc->S_d);           /* current_pot: float32 (closest_dist_sq @ sample_weight) */
   for (int c = 1; c < k; ++c) {
+    /* rand_vals = uniform(size=L) * current_pot (float64); candidate_ids = searchsorted(cumsum_f32, rand_vals),
+     * clipped to n-1.  np.cumsum of a float32 array adds sequentially in float32. */
+    double v[16];
+    int cand[16], found[16], pending = L;
+    for (int t = 0; t < L; ++t) { v[t] = u[1 + (c - 1) * L + t] * (double)pot; cand[t] = n - 1; found[t] = 0; }
+    float S = 0.f;
+    for (int i = 0; i < n && pending; ++i) {
+      S = S + closest[i];
+      for (int t = 0; t < L; ++t)
+        if (!found[t] && (double)S >= v[t]) { cand[t] = i; found[t] = 1; --pending; }
+    }
     int best_cand = -1;
-    int64_t best_pot = 0;
+    float best_pot = 0.f;
     for (int t = 0; t < L; ++t) {
-      const double T = u[1 + (c - 1) * L + t] * (double)pot;
-      int64_t Tq = (int64_t)ceil(T);
-      /* searchsorted(cumsum, T, side='left'), clipped to n-1 */
-      int cand = n - 1;
-      int64_t pre = 0;
-      for (int i = 0; i < n; ++i) {
-        pre += to_fixed(closest[i], sc->S_d);
-        if (pre >= Tq) { cand = i; break; }
-      }
       int64_t p = 0;
-      for (int i = 0; i < n; ++i) {
-        const float d = sqdist(X + (size_t)i * C, X + (size_t)cand * C, C);
-        p += to_fixed(fminf(closest[i], d), sc->S_d);
-      }
-      if (t == 0 || p < best_pot) { best_pot = p; best_cand = cand; }
+      const float* xc = X + (size_t)cand[t] * C;
+      for (int i = 0; i < n; ++i)
+        p += to_fixed(fminf(closest[i], sqdist_upcast(xc, xx[cand[t]], X + (size_t)i * C, xx[i], C)), sc->S_d);
+      const float pf = pot_to_float(p, sc->S_d);     /* candidates_pot is float32; np.argmin: first lowest */
+      if (t == 0 || pf < best_pot) { best_pot = pf; best_cand = cand[t]; }
     }
-    for (int i = 0; i < n; ++i) {
-      const float d = sqdist(X + (size_t)i * C, X + (size_t)best_cand * C, C);
-      closest[i] = fminf(closest[i], d);
-    }
+    const float* xb = X + (size_t)best_cand * C;
+    for (int i = 0; i < n; ++i)
+      closest[i] = fminf(closest[i], sqdist_upcast(xb, xx[best_cand], X + (size_t)i * C, xx[i], C));
     pot = best_pot;
     idx_out[c] = best_cand;
   }
-  (void)cand_d;
 }
 
 /* One Lloyd run from `centers` (k x C, overwritten with the final centres).
@@ -299,6 +332,8 @@ int isa_km_oracle_fit(const float* X_in, int n, int C, int k, int n_init, int ma
   if (tol_abs_out) *tol_abs_out = tol_abs;
   const int L = 2 + (int)log((double)k);
   const int per = 1 + (k - 1) * L;
+  double* xx = (double*)malloc(sizeof(double) * n);
+  for (int i = 0; i < n; ++i) xx[i] = sqnorm64(X + (size_t)i * C, C);
   int* all_labels = (int*)malloc(sizeof(int) * (size_t)n * n_init);
   float* all_centers = (float*)malloc(sizeof(float) * (size_t)k * C * n_init);
   int64_t* inq = (int64_t*)malloc(sizeof(int64_t) * n_init);
@@ -313,7 +348,7 @@ int isa_km_oracle_fit(const float* X_in, int n, int C, int k, int n_init, int ma
       }
     } else {
       float* closest = (float*)malloc(sizeof(float) * n);
-      isa_km_oracle_seed(X, n, C, k, L, uniforms + (size_t)r * per, &sc, idx, closest, NULL);
+      isa_km_oracle_seed(X, n, C, k, L, uniforms + (size_t)r * per, &sc, idx, closest, xx);
       free(closest);
       for (int j = 0; j < k; ++j) memcpy(centers + (size_t)j * C, X + (size_t)idx[j] * C, sizeof(float) * C);
     }
@@ -328,6 +363,6 @@ int isa_km_oracle_fit(const float* X_in, int n, int C, int k, int n_init, int ma
   for (int j = 0; j < k; ++j)
     for (int f = 0; f < C; ++f) centers_out[j * C + f] = all_centers[((size_t)best * k + j) * C + f] + mean[f];
   *best_out = best;
-  free(X); free(mean); free(all_labels); free(all_centers); free(inq);
+  free(X); free(mean); free(all_labels); free(all_centers); free(inq); free(xx);
   return 0;
 }

@@ -21,6 +21,18 @@ KM_CASES = [
 ]
 
 
+# Network embeddings: foreground embeddings of the seed-23 random-init ReSeg network on synth.leaf_image(0) / (2) at the
+# CVPPP size, dumped on the B200 by tools/ncu_infer.py (every 6th point, rounded to float16 to keep the fixture small;
+# the float32 upcast of the stored values IS the input).  Near-tied, unlike the planted clusters above: the picks of
+# k-means++ depend on the float32 rounding of scikit-learn's cumulative sums here.
+NET_CASES = [("net0", 16, 35, 0), ("net2", 16, 35, 0)]
+
+
+def net_inputs(name):
+    d = np.load(os.path.join(HERE, "kmeans_net_inputs.npz"))
+    return d[name + "_X16"].astype(np.float32)
+
+
 def case_inputs(case):
     name, seed, C, H, W, k, pull, n_init, km_seed = case
     d = synth.batch(seed, 1, C, H, W, max(k, 2), n_min=k, n_max=k, pull=pull)
@@ -45,6 +57,12 @@ def main():
             labs.append(KMeans(n_clusters=k, init=c, n_init=1, max_iter=500).fit_predict(X))
         out[name + "_inits"] = np.stack(inits).astype(np.float32)
         out[name + "_init_labels"] = np.stack(labs).astype(np.uint8)
+        print(name, X.shape, "sklearn clusters", len(np.unique(out[name + "_sk_labels"])))
+    for name, k, n_init, km_seed in NET_CASES:
+        X = net_inputs(name)
+        out[name + "_sk_labels"] = KM.sklearn_fit_predict(X, k, km_seed, n_init).astype(np.uint8)
+        _, idx = kmeans_plusplus(X - X.mean(axis=0), k, random_state=km_seed)    # the first restart's picks
+        out[name + "_sk_first_seeds"] = idx.astype(np.int32)
         print(name, X.shape, "sklearn clusters", len(np.unique(out[name + "_sk_labels"])))
     np.savez_compressed(os.path.join(HERE, "kmeans.npz"), **out)
 

@@ -13,7 +13,7 @@ from isa_b200 import synth
 from oracle import kmeans as KM
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-from make_golden_kmeans import KM_CASES, case_inputs  # noqa: E402
+from make_golden_kmeans import KM_CASES, NET_CASES, case_inputs, net_inputs  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +49,37 @@ def test_bit_exact_vs_oracle_and_sklearn_golden(cuda, golden_dir, case):
     for r in range(inits.shape[0]):
         lab_r, _ = _gpu_fit(cuda, X, k, n_init=1, init_centers=inits[r:r + 1])
         assert KM.same_up_to_permutation(lab_r, g[name + "_init_labels"][r])
+
+
+@pytest.mark.parametrize("case", NET_CASES, ids=[c[0] for c in NET_CASES])
+def test_network_embeddings_bit_exact_and_sklearn_golden(cuda, golden_dir, case):
+    """Near-tied random-init network embeddings: scikit-learn's seeds, scikit-learn's partition."""
+    name, k, n_init, km_seed = case
+    g = np.load(os.path.join(golden_dir, "kmeans.npz"))
+    X = net_inputs(name)
+    o = KM.kmeans_oracle(X, k, seed=km_seed, n_init=n_init)
+    labels, res = _gpu_fit(cuda, X, k, seed=km_seed, n_init=n_init)
+    _assert_same_as_oracle(labels, res, o)
+    assert np.array_equal(res.seed_idx.cpu().numpy()[0], g[name + "_sk_first_seeds"])
+    assert KM.same_up_to_permutation(labels, g[name + "_sk_labels"])
+
+
+def test_cumsum_search_edge_cases(cuda):
+    """The parallel float32 running-sum search against the oracle's sequential loop on inputs that stress it: exact ties
+    (dyadic coordinates), long runs of zero distances (duplicates of the first centre), a heavy tail, a point count that
+    is not a multiple of anything, fewer CTAs than restarts."""
+    rs = np.random.RandomState(3)
+    cases = []
+    cases.append(((rs.randint(0, 8, size=(9001, 4)) / 4.0).astype(np.float32), 6, 9))
+    X = rs.standard_normal((20011, 6)).astype(np.float32)
+    X[:5000] = X[0]
+    cases.append((X, 5, 12))
+    cases.append((np.exp(3 * rs.standard_normal((33333, 3))).astype(np.float32), 7, 8))
+    cases.append((rs.standard_normal((300, 2)).astype(np.float32), 4, 35))
+    for X, k, n_init in cases:
+        o = KM.kmeans_oracle(X, k, seed=1, n_init=n_init, max_iter=5)
+        labels, res = _gpu_fit(cuda, X, k, seed=1, n_init=n_init, max_iter=5)
+        _assert_same_as_oracle(labels, res, o)
 
 
 @pytest.mark.parametrize("n,C,k,n_init", [(1000, 3, 1, 2), (5000, 5, 7, 4), (40000, 24, 16, 6), (20000, 32, 64, 2),

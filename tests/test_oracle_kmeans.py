@@ -10,7 +10,7 @@ import pytest
 from oracle import kmeans as KM
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-from make_golden_kmeans import KM_CASES, case_inputs  # noqa: E402
+from make_golden_kmeans import KM_CASES, NET_CASES, case_inputs, net_inputs  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -38,6 +38,47 @@ def test_full_fit_matches_sklearn(golden, case):
     _, X = KM.gather_foreground(sem, emb)
     o = KM.kmeans_oracle(X, k, seed=km_seed, n_init=n_init)
     assert KM.same_up_to_permutation(o["labels"], golden[name + "_sk_labels"]), name
+
+
+@pytest.mark.parametrize("case", NET_CASES, ids=[c[0] for c in NET_CASES])
+def test_network_embeddings_match_sklearn(golden, case):
+    """Near-tied embeddings of a random-init network (dumped on the B200): the picks of k-means++ depend on the float32
+    rounding of scikit-learn's sequential cumulative sums there.  The oracle draws scikit-learn's seeds and ends in
+    scikit-learn's partition."""
+    name, k, n_init, km_seed = case
+    X = net_inputs(name)
+    o = KM.kmeans_oracle(X, k, seed=km_seed, n_init=n_init)
+    assert np.array_equal(o["seed_idx"][0], golden[name + "_sk_first_seeds"]), "k-means++ picks of the first restart"
+    assert KM.same_up_to_permutation(o["labels"], golden[name + "_sk_labels"]), name
+
+
+def test_seeding_is_numpy_restatement_of_sklearn():
+    """isa_km_oracle_seed == _kmeans_plusplus restated with scikit-learn's own distance function and numpy's float32
+    cumsum, with the potentials rounded from exact sums (the one quantity scikit-learn leaves to BLAS)."""
+    from sklearn.metrics.pairwise import _euclidean_distances
+    X = net_inputs("net0")[:3000]
+    k, R = 8, 4
+    n = len(X)
+    Xc = X - X.astype(np.float64).mean(axis=0).astype(np.float32)
+    o = KM.kmeans_oracle(X, k, seed=5, n_init=R, max_iter=1)
+    rs = np.random.RandomState(5)
+    L = KM.n_local_trials(k)
+    for r in range(R):
+        # RandomState.choice(n, p=uniform) consumes one double: searchsorted(cumsum(p), u, side='right')
+        u = rs.random_sample()
+        c0 = int(np.searchsorted(np.arange(1, n + 1) / n, u, side="right"))
+        picks = [min(c0, n - 1)]
+        cd = _euclidean_distances(Xc[picks[0]][None], Xc, squared=True)
+        pot = np.float32(cd.astype(np.float64).sum())
+        for c in range(1, k):
+            rv = rs.random_sample(L) * pot
+            cand = np.minimum(np.searchsorted(np.cumsum(cd[0]), rv), n - 1)
+            d = np.minimum(cd, _euclidean_distances(Xc[cand], Xc, squared=True))
+            cp = d.astype(np.float64).sum(axis=1).astype(np.float32)
+            b = int(np.argmin(cp))
+            pot, cd = cp[b], d[b][None]
+            picks.append(int(cand[b]))
+        assert picks == list(o["seed_idx"][r]), r
 
 
 def test_uniform_stream_is_what_sklearn_consumes():
