@@ -83,6 +83,26 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
   }
   __syncthreads();
 }
+// Variant for barriers behind which a few CTAs work for a long time while the rest wait (the k-means++ candidate search:
+// 35 of 256 CTAs): the waiters poll with RELAXED loads and back off, and fence once at the end.  ld.acquire.gpu compiles
+// to LDG.STRONG + CCTL.IVALL; a waiter that invalidates its SM's L1 every ~100 ns slowed the working CTA on the same SM.
+__device__ __forceinline__ void group_barrier_patient(unsigned* counter, unsigned target) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1u);
+    unsigned ns = 64;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      __nanosleep(ns);
+      if (ns < 1024) ns *= 2;
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 // Leaner variant (the cooperative-groups pattern): bar.sync orders the CTA's writes before thread 0, whose
 // gpu-scope fence + release-arrive publishes them (fence cumulativity); no per-thread fence, no sleep in the poll.
 __device__ __forceinline__ void group_barrier_lean(unsigned* counter, unsigned target) {

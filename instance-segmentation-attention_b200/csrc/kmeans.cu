@@ -59,6 +59,7 @@ struct KmWs {
   long long* seed_pot;     // [k][R][kMaxL] potentials of the candidates of every k-means++ step (atomically summed)
   unsigned* gen;           // [R] flow kernel: published Lloyd iteration of the restart | state << 24
   unsigned* done;          // [R] flow kernel: slices that have finished their E-step, summed over the iterations
+  unsigned long long* seed_prof;   // [6] CTA 0's phase times of the seeding kernel in ns: search, pass 1, pass 2, grid barriers; its search segments, rounds
   size_t zero_bytes;
   // not zeroed
   float* mean;             // [C]
@@ -97,6 +98,7 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.seed_pot = (long long*)take(8 * (size_t)k * R * kMaxL);
   w.gen = (unsigned*)take(4 * (size_t)R);
   w.done = (unsigned*)take(4 * (size_t)R);
+  w.seed_prof = (unsigned long long*)take(8 * 6);
   w.zero_bytes = off;
   w.mean = (float*)take(4 * (size_t)C);
   w.Xc = (float*)take(4 * (size_t)C * ld);
@@ -301,10 +303,11 @@ struct ScanShared {
   unsigned wsum[kSeedThreads / 32][2];
   int wbad[kSeedThreads / 32];
   int hit[kMaxL];
-  float hit_s[kMaxL];
-  float s, s_new;
-  int pos;
-  unsigned pending;
+  float s;              // running sum after everything consumed so far
+  int pos;              // first element of the current round
+  int lane0;            // first thread of the round whose run is not consumed yet
+  unsigned pending;     // thresholds not crossed yet
+  unsigned nseg, nround;   // diagnostics: segments / rounds of all searches of this CTA
 };
 
 __device__ __forceinline__ unsigned scan_sat_add(unsigned a, unsigned b) {
@@ -312,153 +315,166 @@ __device__ __forceinline__ unsigned scan_sat_add(unsigned a, unsigned b) {
   return s > kScanSat ? kScanSat : s;
 }
 
-// One run of up to 32 elements from `pos` with real float32 adds (warp 0, all lanes in lockstep).
-// Crossed thresholds are written to out[] and removed from `pending`.
-__device__ __forceinline__ void scan_replay_run(const float* __restrict__ cl, int n, int pos, float& S, const double* v, int L,
-                                                unsigned& pending, int* out) {
-  const int lane = threadIdx.x & 31;
-  const int i = pos + lane;
-  const float xv = (i < n) ? __ldcg(cl + i) : 0.f;
-  const int cnt = (n - pos) < kScanRun ? (n - pos) : kScanRun;
-  for (int j = 0; j < cnt; ++j) {
-    S = __fadd_rn(S, __shfl_sync(0xffffffffu, xv, j));
-    if (pending) {
-      const double Sd = (double)S;
-      for (int t = 0; t < L; ++t)
-        if (((pending >> t) & 1u) && Sd >= v[t]) {
-          if (lane == 0) out[t] = pos + j;
-          pending &= ~(1u << t);
-        }
+// The running sum s2 has reached the lowest pending threshold at element idx: record every threshold of `pend` that is
+// crossed, take it out of *pending_word, and return {float bits of the next lowest threshold (rounded up: for a float s,
+// (double)s >= v  <=>  s >= float_ru(v)), remaining thresholds}.  Out of line: it runs a handful of times per search.
+__device__ __noinline__ uint2 scan_cross(float s2, int idx, unsigned pend, const double* v, int L, int* out, unsigned* pending_word) {
+  double vmin = __longlong_as_double(0x7ff0000000000000ll);
+  const double sd = (double)s2;
+  for (int t = 0; t < L; ++t)
+    if ((pend >> t) & 1u) {
+      if (sd >= v[t]) {
+        out[t] = idx;
+        pend &= ~(1u << t);
+        atomicAnd(pending_word, ~(1u << t));
+      } else {
+        vmin = fmin(vmin, v[t]);
+      }
     }
-  }
+  return make_uint2(__float_as_uint(__double2float_ru(vmin)), pend);
 }
 
 // out[t] = first i with (double)S_i >= v[t], else n - 1 (np.searchsorted(..., side='left') clipped).  Whole CTA.
+// A round = 8192 elements, 32 per thread, loaded ONCE into registers; inside a round the runs are consumed in segments:
+// quantise the not yet consumed runs on the grid of the current binade, scan, accept the prefix up to the first run that
+// leaves the binade, let the thread that owns that run replay it with real FADDs from its registers (it knows its exact
+// start value), and continue behind it on the new grid.  The thread owning the run that crosses a threshold resolves
+// the index the same way.
 __device__ void seq_cumsum_search_cta(const float* __restrict__ cl, int n, const double* v, int L, int* out, ScanShared& sh) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kSeedThreads / 32;
   __syncthreads();
-  if (tid == 0) { sh.s = 0.f; sh.pos = 0; sh.pending = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u); }
+  if (tid == 0) { sh.s = 0.f; sh.pos = 0; sh.lane0 = 0; sh.pending = (1u << L) - 1u; }
   if (tid < L) out[tid] = n - 1;
   __syncthreads();
   while (true) {
-    const float S = sh.s;
     const int pos = sh.pos;
-    const unsigned pending = sh.pending;
-    if (pos >= n || !pending) break;
-    if (!(S >= 0x1p-100f)) {
-      // no usable grid yet (zero / tiny running sum): one run with real adds
-      __syncthreads();                            // everyone has read the state
-      if (warp == 0) {
-        float s2 = S;
-        unsigned p2 = pending;
-        scan_replay_run(cl, n, pos, s2, v, L, p2, out);
-        if (lane == 0) { sh.s = s2; sh.pos = pos + kScanRun; sh.pending = p2; }
-      }
-      __syncthreads();
-      continue;
-    }
-    const int e = (int)((__float_as_uint(S) >> 23) & 0xffu) - 127;
-    const float scale = __uint_as_float((unsigned)(127 + 23 - e) << 23);   // 1 / u
-    const float inv = __uint_as_float((unsigned)(127 - 23 + e) << 23);     // u
-    const unsigned m = (unsigned)__fmul_rn(S, scale);                      // exact, in [2^23, 2^24)
-    if (tid < L) sh.hit[tid] = 0x7fffffff;
-    // ---- this thread's run: (increment from an even start, increment from an odd start)
+    if (pos >= n || !sh.pending) break;
+    if (tid == 0) ++sh.nround;
+    // ---- this thread's run of the round
     const int i0 = pos + tid * kScanRun;
-    unsigned ie = 0, io = 0;
-    bool big = false;
-    if (i0 < n) {
-      float xv[kScanRun];
-      if (i0 + kScanRun <= n && ((reinterpret_cast<size_t>(cl + i0) & 15) == 0)) {
+    float xv[kScanRun];
+    if (i0 + kScanRun <= n && ((reinterpret_cast<size_t>(cl + i0) & 15) == 0)) {
 #pragma unroll
-        for (int j4 = 0; j4 < kScanRun / 4; ++j4) {
-          const float4 q = __ldcg(reinterpret_cast<const float4*>(cl + i0) + j4);
-          xv[4 * j4] = q.x; xv[4 * j4 + 1] = q.y; xv[4 * j4 + 2] = q.z; xv[4 * j4 + 3] = q.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < kScanRun; ++j) xv[j] = (i0 + j < n) ? __ldcg(cl + i0 + j) : 0.f;
+      for (int j4 = 0; j4 < kScanRun / 4; ++j4) {
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(cl + i0) + j4);
+        xv[4 * j4] = q.x; xv[4 * j4 + 1] = q.y; xv[4 * j4 + 2] = q.z; xv[4 * j4 + 3] = q.w;
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kScanRun; ++j) xv[j] = (i0 + j < n) ? __ldcg(cl + i0 + j) : 0.f;
+    }
+    // real float32 adds over this thread's run (registers) from `s0`; the hot path is FADD + one compare per element
+    auto replay = [&](float s0, unsigned pend) {
+      float s2 = s0;
+      double vmin = __longlong_as_double(0x7ff0000000000000ll);
+      for (int t = 0; t < L; ++t)
+        if ((pend >> t) & 1u) vmin = fmin(vmin, v[t]);
+      float vf = __double2float_ru(vmin);
 #pragma unroll
       for (int j = 0; j < kScanRun; ++j) {
-        const float t = __fmul_rn(xv[j], scale);  // exact scaling (a denormal result rounds to < 0.5: increment 0 either way)
-        if (!(t < 16777216.f)) big = true;        // the element does not fit the grid of this binade
-        else {
-          const unsigned a = (unsigned)t;         // floor
-          const float f = __fsub_rn(t, (float)a); // exact
-          const unsigned base = a + (f > 0.5f ? 1u : 0u);
-          const bool tie = (f == 0.5f);
-          ie += base + (tie ? ((ie + a) & 1u) : 0u);
-          io += base + (tie ? ((1u + io + a) & 1u) : 0u);
+        s2 = __fadd_rn(s2, xv[j]);                 // elements beyond n are zeros: they cannot cross anything
+        if (s2 >= vf) {
+          const uint2 r = scan_cross(s2, i0 + j, pend, v, L, out, &sh.pending);
+          vf = __uint_as_float(r.x);
+          pend = r.y;
         }
       }
-    }
-    // ---- inclusive warp scan of the pairs (the shuffled-in value is the EARLIER segment)
-    unsigned pe = ie, po = io;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned ae = __shfl_up_sync(0xffffffffu, pe, o), ao = __shfl_up_sync(0xffffffffu, po, o);
-      if (lane >= o) {
-        const unsigned ne = scan_sat_add(ae, (ae & 1u) ? po : pe);
-        const unsigned no = scan_sat_add(ao, ((1u + ao) & 1u) ? po : pe);
-        pe = ne; po = no;
+      return s2;
+    };
+    // ---- segments of the round
+    while (true) {
+      __syncthreads();                                                         // state of the previous segment is visible
+      const float S = sh.s;
+      const int lane0 = sh.lane0;
+      const unsigned pending = sh.pending;
+      if (lane0 >= NW * 32 || pos + lane0 * kScanRun >= n || !pending) break;
+      __syncthreads();                                                         // everyone has read the state
+      if (tid == 0) ++sh.nseg;
+      if (!(S >= 0x1p-100f)) {
+        // no usable grid yet (zero / tiny running sum): the owner of the next run replays it
+        if (tid == lane0) { sh.s = replay(S, pending); sh.lane0 = lane0 + 1; }
+        continue;
       }
-    }
-    if (lane == 31) { sh.wsum[warp][0] = pe; sh.wsum[warp][1] = po; }
-    __syncthreads();                                                           // A
-    unsigned mw = m;                                                           // m at the start of this warp's elements
-    for (int w2 = 0; w2 < warp; ++w2) mw = scan_sat_add(mw > kScanSat ? kScanSat : mw, (mw & 1u) ? sh.wsum[w2][1] : sh.wsum[w2][0]);
-    const unsigned m_after = scan_sat_add(mw > kScanSat ? kScanSat : mw, (mw & 1u) ? po : pe);
-    unsigned m_before = __shfl_up_sync(0xffffffffu, m_after, 1);
-    if (lane == 0) m_before = mw;
-    const bool bad = big || m_after >= kScanLimit;
-    const unsigned badmask = __ballot_sync(0xffffffffu, bad);
-    if (lane == 0) sh.wbad[warp] = badmask ? (__ffs(badmask) - 1) : 32;
-    __syncthreads();                                                           // B
-    int valid = NW * 32;
-    for (int w2 = NW - 1; w2 >= 0; --w2)
-      if (sh.wbad[w2] < 32) valid = w2 * 32 + sh.wbad[w2];
-    // ---- thresholds crossed inside the valid prefix: S_i >= v  <=>  m_i >= v / u
-    for (int t = 0; t < L; ++t) {
-      if (!((pending >> t) & 1u)) continue;
-      const double need = __dmul_rn(v[t], (double)scale);
-      const unsigned hm = __ballot_sync(0xffffffffu, tid < valid && (double)m_after >= need);
-      if (hm && lane == 0) atomicMin(&sh.hit[t], warp * 32 + (__ffs(hm) - 1));
-    }
-    __syncthreads();                                                           // C
-    for (int t = 0; t < L; ++t)
-      if (sh.hit[t] == tid) sh.hit_s[t] = __fmul_rn((float)m_before, inv);
-    if (valid > 0 && tid == valid - 1) sh.s_new = __fmul_rn((float)m_after, inv);
-    __syncthreads();                                                           // D
-    if (warp == 0) {
-      unsigned p2 = pending;
-      for (int t = 0; t < L; ++t) {
-        const int h = sh.hit[t];
-        if (!((p2 >> t) & 1u) || h == 0x7fffffff) continue;
-        float s2 = sh.hit_s[t];
-        // replay the run that crosses v[t] from its exact start value (only threshold t is looked at)
-        const int rpos = pos + h * kScanRun;
-        const int i = rpos + lane;
-        const float xv = (i < n) ? __ldcg(cl + i) : 0.f;
-        const int cnt = (n - rpos) < kScanRun ? (n - rpos) : kScanRun;
-        for (int j = 0; j < cnt; ++j) {
-          s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, xv, j));
-          if ((double)s2 >= v[t]) {
-            if (lane == 0) out[t] = rpos + j;
-            break;
+      const int e = (int)((__float_as_uint(S) >> 23) & 0xffu) - 127;
+      const float scale = __uint_as_float((unsigned)(127 + 23 - e) << 23);   // 1 / u
+      const float inv = __uint_as_float((unsigned)(127 - 23 + e) << 23);     // u
+      const unsigned m = (unsigned)__fmul_rn(S, scale);                      // exact, in [2^23, 2^24)
+      if (tid < L) sh.hit[tid] = 0x7fffffff;
+      // (increment from an even start, increment from an odd start) of this thread's run on the grid u
+      unsigned ie = 0, io = 0;
+      bool big = false;
+      if (tid >= lane0 && i0 < n) {
+#pragma unroll
+        for (int j = 0; j < kScanRun; ++j) {
+          const float t = __fmul_rn(xv[j], scale);  // exact scaling (a denormal result rounds to 0: increment 0 either way)
+          if (!(t < 8388607.f)) big = true;         // rint(t) must fit 23 bits; such an element (x >= ~S / 2) gets a real add
+          else {
+            // r = rint(t) without a conversion instruction: the mantissa of t + 2^23; fr = t - r in [-1/2, 1/2], exact
+            const float tr = __fadd_rn(t, 8388608.f);
+            const unsigned r = __float_as_uint(tr) & 0x7fffffu;
+            const float fr = __fsub_rn(t, __fsub_rn(tr, 8388608.f));
+            // m + t rounds to m + r unless it is a tie (|fr| = 1/2, r even) and m is odd: then to the even neighbour r +- 1
+            const unsigned adj = (fr == 0.5f) ? 1u : ((fr == -0.5f) ? 0xffffffffu : 0u);
+            ie += r + ((ie & 1u) ? adj : 0u);
+            io += r + (((1u + io) & 1u) ? adj : 0u);
           }
         }
-        p2 &= ~(1u << t);
       }
-      float s2 = valid > 0 ? sh.s_new : S;
-      int pos2 = pos + valid * kScanRun;
-      if (valid < NW * 32 && pos2 < n && p2) {
-        scan_replay_run(cl, n, pos2, s2, v, L, p2, out);   // the run that leaves the binade
-        pos2 += kScanRun;
+      // inclusive warp scan of the pairs (the shuffled-in value is the EARLIER segment)
+      unsigned pe = ie, po = io;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned ae = __shfl_up_sync(0xffffffffu, pe, o), ao = __shfl_up_sync(0xffffffffu, po, o);
+        if (lane >= o) {
+          const unsigned ne = scan_sat_add(ae, (ae & 1u) ? po : pe);
+          const unsigned no = scan_sat_add(ao, ((1u + ao) & 1u) ? po : pe);
+          pe = ne; po = no;
+        }
       }
-      if (lane == 0) { sh.s = s2; sh.pos = pos2; sh.pending = p2; }
+      if (lane == 31) { sh.wsum[warp][0] = pe; sh.wsum[warp][1] = po; }
+      __syncthreads();                                                         // A
+      unsigned mw = m;                                                         // m at the start of this warp's runs
+      for (int w2 = 0; w2 < warp; ++w2) mw = scan_sat_add(mw, (mw & 1u) ? sh.wsum[w2][1] : sh.wsum[w2][0]);
+      const unsigned m_after = scan_sat_add(mw, (mw & 1u) ? po : pe);
+      unsigned m_before = __shfl_up_sync(0xffffffffu, m_after, 1);
+      if (lane == 0) m_before = mw;
+      const bool bad = (tid >= lane0) && (big || m_after >= kScanLimit);
+      const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+      if (lane == 0) sh.wbad[warp] = badmask ? (__ffs(badmask) - 1) : 32;
+      __syncthreads();                                                         // B
+      int valid = NW * 32;                                                     // first thread whose run leaves the grid
+      for (int w2 = NW - 1; w2 >= 0; --w2)
+        if (sh.wbad[w2] < 32) valid = w2 * 32 + sh.wbad[w2];
+      // thresholds crossed inside the accepted prefix: S_i >= v  <=>  m_i >= v / u
+      for (int t = 0; t < L; ++t) {
+        if (!((pending >> t) & 1u)) continue;
+        const double need = __dmul_rn(v[t], (double)scale);
+        const unsigned hm = __ballot_sync(0xffffffffu, tid >= lane0 && tid < valid && (double)m_after >= need);
+        if (hm && lane == 0) atomicMin(&sh.hit[t], warp * 32 + (__ffs(hm) - 1));
+      }
+      __syncthreads();                                                         // C
+      // owners: the runs that cross a threshold (only that threshold is resolved there), the run that leaves the grid
+      unsigned mine = 0;
+      for (int t = 0; t < L; ++t)
+        if (sh.hit[t] == tid) mine |= 1u << t;
+      if (mine) replay(__fmul_rn((float)m_before, inv), mine);
+      if (tid == valid) {
+        // thresholds already owned by an earlier run were taken out of `pending` by their owners (atomicAnd) or are
+        // being taken out right now; this run only looks at those that no accepted run crosses
+        unsigned rest = pending;
+        for (int t = 0; t < L; ++t)
+          if (sh.hit[t] != 0x7fffffff) rest &= ~(1u << t);
+        sh.s = replay(valid == lane0 ? S : __fmul_rn((float)m_before, inv), rest);
+        sh.lane0 = valid + 1;
+      } else if (valid == NW * 32 && tid == NW * 32 - 1) {
+        sh.s = __fmul_rn((float)m_after, inv);
+        sh.lane0 = NW * 32;
+      }
     }
-    __syncthreads();                                                           // E
+    __syncthreads();
+    if (tid == 0) { sh.pos = pos + NW * 32 * kScanRun; sh.lane0 = 0; }
+    __syncthreads();
   }
   __syncthreads();
 }
@@ -573,6 +589,11 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
   }
   grid_barrier(ws.seed_barrier, epoch);
 
+  // CTA 0 keeps a coarse phase profile (ns): search, pass 1, pass 2, the three grid barriers
+  if (threadIdx.x == 0) { s_scan.nseg = 0; s_scan.nround = 0; }
+  unsigned long long t_s = 0, t_p1 = 0, t_p2 = 0, t_bar = 0, t_mark = gtime_ns();
+  auto lap = [&](unsigned long long& acc) { const unsigned long long t = gtime_ns(); acc += t - t_mark; t_mark = t; };
+
   for (int c = 1; c < k; ++c) {
     // ---- search: CTA (r mod G) draws the L candidates of restart r
     for (int r = b; r < R; r += G) {
@@ -592,7 +613,10 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       __syncthreads();
       seq_cumsum_search_cta(ws.closest + (size_t)r * ld, n, s_v, L, ws.seed_cand + (size_t)r * L, s_scan);
     }
-    grid_barrier(ws.seed_barrier, epoch);
+    lap(t_s);
+    epoch += 1;
+    group_barrier_patient(ws.seed_barrier, epoch * gridDim.x);
+    lap(t_bar);
 
     // ---- pass 1: potential of every candidate over this CTA's points
     for (int pair = threadIdx.x; pair < RL; pair += kSeedThreads) s_cidx[pair] = __ldcg(ws.seed_cand + pair);
@@ -648,7 +672,9 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + pair];
       if (t) atomicAdd((unsigned long long*)(pot_c + (pair / L) * kMaxL + pair % L), (unsigned long long)t);
     }
+    lap(t_p1);
     grid_barrier(ws.seed_barrier, epoch);
+    lap(t_bar);
 
     // ---- best trial per restart (candidates_pot is float32; np.argmin: first lowest); pass 2: closest = min(closest,
     //      d(best)), new per-CTA totals
@@ -706,10 +732,14 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       for (int w = 0; w < NW; ++w) t += s_pot[(size_t)w * RL + r * L];
       ws.seed_tot[(size_t)r * kSeedMaxCtas + b] = t;
     }
+    lap(t_p2);
     grid_barrier(ws.seed_barrier, epoch);
+    lap(t_bar);
   }
   // centres of every restart = the picked rows (CTA 0 wrote seed_idx itself)
   if (b == 0) {
+    if (threadIdx.x == 0) { ws.seed_prof[0] = t_s; ws.seed_prof[1] = t_p1; ws.seed_prof[2] = t_p2; ws.seed_prof[3] = t_bar;
+                            ws.seed_prof[4] = 1000ull * s_scan.nseg; ws.seed_prof[5] = 1000ull * s_scan.nround; }
     __syncthreads();
     for (int idx = threadIdx.x; idx < R * k * C; idx += kSeedThreads) {
       const int rj = idx / C, f = idx % C;
@@ -1246,6 +1276,7 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
       prm.info[0] = 0; prm.info[1] = best; prm.info[2] = n; prm.info[3] = total_iters;
       prm.info[4] = (int)(t_e / 1000); prm.info[5] = (int)(t_b1 / 1000); prm.info[6] = (int)(t_u / 1000); prm.info[7] = (int)(t_b2 / 1000);
       prm.info[8] = (int)((t_loop_end - t_start) / 1000); prm.info[9] = (int)((gtime_ns() - t_loop_end) / 1000);
+      for (int q = 0; q < 6; ++q) prm.info[10 + q] = (int)(ws.seed_prof[q] / 1000);   // seeding kernel: search, pass 1, pass 2, barriers (us); search segments, rounds
     }
   }
 }

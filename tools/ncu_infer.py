@@ -30,8 +30,8 @@ for j in range(n_img):
     torch.cuda.synchronize()
     res = out[4]
     info = res.info.cpu().numpy() if hasattr(res.info, "cpu") else np.asarray(res.info)
-    print("image %d: n=%d restart-iterations=%d grid-iterations=%d phases(us) E=%d bar1=%d upd=%d bar2=%d loop=%d tail=%d" % (
-        j, int(info[2]), int(res.n_iter.sum()), int(info[3]), info[4], info[5], info[6], info[7], info[8], info[9]))
+    print("image %d: n=%d restart-iterations=%d grid-iterations=%d phases(us) E=%d bar1=%d upd=%d bar2=%d loop=%d tail=%d | seeding(us) search=%d pass1=%d pass2=%d barriers=%d segments=%d rounds=%d" % (
+        j, int(info[2]), int(res.n_iter.sum()), int(info[3]), info[4], info[5], info[6], info[7], info[8], info[9], info[10], info[11], info[12], info[13], info[14], info[15]))
     if dump:
         os.makedirs(dump, exist_ok=True)
         from oracle import kmeans as KM   # diagnostic tool (not product): the oracle's own foreground rule
