@@ -22,6 +22,7 @@
 //                     E-step tiles of every active restart -> grid barrier -> per-restart
 //                     update CTA -> grid barrier; then E-step re-run, inertia, selection.
 #include "isa_common.cuh"
+#include "isa_tcgen05.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -71,8 +72,16 @@ struct KmWs {
   int* seed_idx;           // [R][k]
   long long* seed_tot;     // [R][kSeedMaxCtas] per-CTA totals of closest[] (fixed point)
   int* seed_cand;          // [R][kMaxL] candidate indices of the current step
+  unsigned char* Xa;       // tensor-core E-step: Xc as bf16 hi / lo UMMA operand tiles, [half-tile of 128 points][hi | lo][128 x KP]
+  float* xn;               // [ld] |x|_2 of every centred point, rounded up (error bound of the tensor-core distances)
   size_t total_bytes;
 };
+
+// Tensor-core E-step (km_lloyd_kernel<.., TC = true>): available for C <= 32 and k <= 128.
+__host__ __device__ inline bool km_tc_ok(int C, int k) { return C <= 32 && k <= 128; }
+__host__ __device__ inline int km_tc_kp(int C) { return C <= 16 ? 16 : 32; }                      // K of the MMAs (multiple of 16)
+__host__ __device__ inline int km_tc_halftiles(int ld) { return ((ld + 255) / 256) * 2; }         // 128-point half tiles (even)
+__host__ __device__ inline int km_tc_npad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : 128; }
 
 KmWs km_carve(void* base, int ld, int C, int k, int R) {
   KmWs w;
@@ -109,6 +118,8 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.seed_idx = (int*)take(4 * (size_t)R * k);
   w.seed_tot = (long long*)take(8 * (size_t)R * kSeedMaxCtas);
   w.seed_cand = (int*)take(4 * (size_t)R * kMaxL);
+  w.Xa = (unsigned char*)take(km_tc_ok(C, k) ? (size_t)km_tc_halftiles(ld) * 128 * km_tc_kp(C) * 4 : 0);
+  w.xn = (float*)take(km_tc_ok(C, k) ? 4 * (size_t)ld : 0);
   w.total_bytes = off;
   return w;
 }
@@ -224,6 +235,39 @@ __global__ void km_init_centers_kernel(const float* __restrict__ init, int R, in
     ws.centers[i] = __fsub_rn(init[i], ws.mean[i % C]);
     if (i % C == 0) ws.seed_idx[i / C] = -1;
   }
+}
+
+// Tensor-core operand of the points: every centred row split into bf16 hi + lo (x = hi + lo to ~16 mantissa bits) and
+// written in the canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices), one block of [hi | lo] per 128 points,
+// so that a Lloyd work item of 256 points is ONE bulk copy.  Rows >= n and features >= C are zero.  Also |x|_2 (rounded up).
+__global__ void km_prep_tc_kernel(const int* __restrict__ n_ptr, int ld, int C, int KP, KmWs ws) {
+  const int n = *n_ptr;
+  if (*ws.status) return;
+  const int rows = km_tc_halftiles(ld) * 128;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int gs = (KP / 8) * 128;
+  unsigned char* blk = ws.Xa + (size_t)(row >> 7) * (128 * KP * 4);
+  const int r = row & 127;
+  float nn = 0.f;
+  for (int kc = 0; kc < KP / 8; ++kc) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = kc * 8 + i;
+      v[i] = (row < n && f < C) ? ws.Xc[(size_t)f * ld + row] : 0.f;
+      nn = __fmaf_rn(v[i], v[i], nn);
+    }
+    uint4 hi, lo;
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
+    const int off = (r >> 3) * gs + kc * 128 + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(blk + off) = hi;
+    *reinterpret_cast<uint4*>(blk + 128 * KP * 2 + off) = lo;
+  }
+  if (row < ld) ws.xn[row] = __fmul_rn(__fsqrt_rn(nn), 1.0001f);
 }
 
 // ------------------------------------------------------------------ seeding
@@ -1030,11 +1074,37 @@ __device__ void lloyd_update_restart(const LloydParams& prm, const KmScales& sc,
   __syncthreads();
 }
 
-template <int CP, int PPT>
-__global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kernel(const LloydParams prm) {
-  constexpr int kPPT = PPT;
-  constexpr int kTile = kLloydThreads * PPT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// Shared-memory layout of the tensor-core E-step (bytes from the start of its region, 128 B aligned pieces).
+struct TcLayout {
+  int kp, npad, nb, a_stage, b_part;
+  size_t a, b, cent, csq, thr, lab, amb, moved, total;
+};
+__host__ __device__ inline TcLayout km_tc_layout(int C, int CP, int k) {
+  TcLayout t;
+  t.kp = km_tc_kp(C);
+  t.npad = km_tc_npad(k);
+  t.nb = 128 / t.npad;                                   // restarts per MMA batch: nb * npad = 128 accumulator columns per half
+  t.a_stage = 256 * t.kp * 4;                            // 256 points x (hi + lo) x kp bf16
+  t.b_part = 128 * t.kp * 2;                             // 128 centre rows x kp bf16 (one of hi / lo)
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off += (bytes + 127) / 128 * 128; return r; };
+  t.a = take(2 * (size_t)t.a_stage);
+  t.b = take(2 * (size_t)t.b_part);
+  t.cent = take((size_t)t.nb * k * CP * 4);
+  t.csq = take((size_t)t.nb * t.npad * 4);
+  t.thr = take((size_t)t.nb * 2 * 4);
+  t.lab = take((size_t)t.nb * 256);
+  t.amb = take((size_t)t.nb * 256 * 2);
+  t.moved = take((size_t)t.nb * 256 * 4);
+  t.total = off;
+  return t;
+}
+
+template <int CP, int PPT, bool TC>
+__global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_lloyd_kernel(const LloydParams prm) {
+  constexpr int kPPT = TC ? 1 : PPT;
+  constexpr int kTile = kLloydThreads * kPPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = *prm.n_ptr;
   const int C = prm.C, k = prm.k, R = prm.R, ld = prm.ld;
   const KmWs& ws = prm.ws;
@@ -1045,8 +1115,15 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
   }
   float* s_cent = reinterpret_cast<float*>(smem_raw);                       // [k][CP]
   float* s_csq = s_cent + k * CP;                                           // [k]
-  float* s_cdup = s_csq + (k + 3) / 4 * 4;                                  // [k][CP] x {c, c} (16 B aligned)
-  unsigned* s_moved = reinterpret_cast<unsigned*>(s_cdup + (size_t)2 * k * CP);  // [kTile] (point in tile | old << 12 | new << 20)
+  float* s_cdup = s_csq + (k + 3) / 4 * 4;                                  // [k][CP] x {c, c} (16 B aligned); FFMA E-step only
+  unsigned* s_moved = reinterpret_cast<unsigned*>(s_cdup + (TC ? 0 : (size_t)2 * k * CP));  // [kTile] (point in tile | old << 12 | new << 20)
+  // tensor-core E-step: its own region behind the update's centres
+  unsigned char* tc_base = smem_raw + (((size_t)(k * CP + (k + 3) / 4 * 4) * 4 + 127) / 128) * 128;
+  const TcLayout tl = km_tc_layout(C, CP, k);
+  __shared__ uint64_t s_afull[2], s_mma;
+  __shared__ uint32_t s_tmem;
+  __shared__ unsigned s_namb, s_chg;
+  __shared__ int s_batch_r[8];
   __shared__ int s_nmoved;
   __shared__ int s_active[kMaxInit];
   __shared__ int s_nactive;
@@ -1071,6 +1148,7 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
   // (CAS loops) inside divergent code: every warp with one changed lane paid 2*C serialized atomics, and the
   // E-steps took 9 of the kernel's 10 ms.
   auto run_estep = [&](int mode) {
+   if constexpr (!TC) {
     const int total = s_nactive * tiles;
     // balanced contiguous ranges (sizes differ by at most one item; ceil-sized ranges left up to half the CTAs idle)
     const int it0 = (int)((long long)blockIdx.x * total / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
@@ -1142,6 +1220,243 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
         }
       }
     }
+   }
+  };
+
+  // ---- tensor-core E-step (TC): the distances of 256 points to the centres of up to `nb` restarts are ONE batch of
+  // tcgen05 MMAs (D[128 x nb*npad] per half tile, fp32 in tensor memory; bf16 hi/lo split: x c ~ xh ch + xh cl + xl ch, ~2^-16).
+  // They are a FILTER, not the result: a point whose best and second-best scores are further apart than the error bound
+  // of the tensor-core scores has the same argmin in the oracle's fp32 fmaf arithmetic; the few points inside the bound
+  // are recomputed with exactly that arithmetic.  Labels stay bit-exact, ~95 % of the FFMA work moves to the tensor pipe.
+  unsigned tc_seq = 0;                                    // work items issued so far by this CTA (mbarrier phases)
+  uint32_t tmem = 0;
+  if constexpr (TC) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_afull[0], 1); mbar_init(&s_afull[1], 1); mbar_init(&s_mma, 1);
+      fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem = s_tmem;
+  }
+  auto run_estep_tc = [&](int mode) {
+    if constexpr (TC) {
+      const int KP = tl.kp, NPAD = tl.npad, NB = tl.nb;
+      const int gs = (KP / 8) * 128;
+      unsigned char* tc_a = tc_base + tl.a;
+      unsigned char* tc_b = tc_base + tl.b;
+      float* tc_cent = reinterpret_cast<float*>(tc_base + tl.cent);       // [NB][k][CP]
+      float* tc_csq = reinterpret_cast<float*>(tc_base + tl.csq);         // [NB][NPAD] (+huge beyond k)
+      float* tc_thr = reinterpret_cast<float*>(tc_base + tl.thr);         // [NB][2]: ambiguity bound = thr0 * |x| + thr1
+      unsigned char* tc_lab = tc_base + tl.lab;                           // [NB][256]
+      unsigned short* tc_amb = reinterpret_cast<unsigned short*>(tc_base + tl.amb);   // point | slot << 8
+      unsigned* tc_moved = reinterpret_cast<unsigned*>(tc_base + tl.moved);           // point | old << 8 | new << 16 | slot << 24
+      const int tid = threadIdx.x;
+      const int nact = s_nactive;
+      const int nbat = (nact + NB - 1) / NB;
+      const int total = nbat * tiles;
+      const int it0 = (int)((long long)blockIdx.x * total / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+      const uint32_t el = elect_one();
+      auto issue_load = [&](int tile, unsigned seq) {
+        const unsigned st = seq & 1u;
+        mbar_arrive_expect_tx(&s_afull[st], (uint32_t)tl.a_stage);
+        tma_bulk_g2s(tc_a + (size_t)st * tl.a_stage, ws.Xa + (size_t)tile * tl.a_stage, (uint32_t)tl.a_stage, &s_afull[st]);
+      };
+      if (it0 < it1 && tid == 0) issue_load(it0 % tiles, tc_seq);
+      int cur_b = -1, nbq = 0;
+      const int half = tid >> 7;                                           // which 128-point half of the tile this thread reads
+      const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)half * 128u;
+      for (int item = it0; item < it1; ++item) {
+        const int bi = item / tiles, tile = item % tiles;
+        if (bi != cur_b) {
+          // ---- centres of the batch: fp32 copy (exact path), |c|^2, bf16 hi / lo B operand, error-bound coefficients
+          __syncthreads();
+          cur_b = bi;
+          nbq = nact - bi * NB < NB ? nact - bi * NB : NB;
+          if (tid < 8) s_batch_r[tid] = tid < nbq ? s_active[bi * NB + tid] : 0;
+          __syncthreads();
+          for (int idx = tid; idx < nbq * k * CP; idx += kLloydThreads) {
+            const int q = idx / (k * CP), rem = idx - q * (k * CP), j = rem / CP, f = rem - j * CP;
+            tc_cent[idx] = (f < C) ? __ldcg(ws.centers + ((size_t)s_batch_r[q] * k + j) * C + f) : 0.f;
+          }
+          __syncthreads();
+          for (int idx = tid; idx < NB * NPAD; idx += kLloydThreads) {
+            const int q = idx / NPAD, j = idx - q * NPAD;
+            float a = 3.0e38f;                                             // padded columns never win
+            if (q < nbq && j < k) {
+              a = 0.f;
+              const float* c = tc_cent + ((size_t)q * k + j) * CP;
+              for (int f = 0; f < C; ++f) a = __fmaf_rn(c[f], c[f], a);
+            }
+            tc_csq[idx] = a;
+          }
+          for (int idx = tid; idx < 128 * (KP / 8); idx += kLloydThreads) {
+            const int row = idx / (KP / 8), kc = idx - row * (KP / 8);
+            const int q = row / NPAD, j = row - q * NPAD;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int f = kc * 8 + i;
+              v[i] = (q < nbq && j < k && f < CP) ? tc_cent[((size_t)q * k + j) * CP + f] : 0.f;
+            }
+            uint4 hi, lo;
+            split2(v[0], v[1], hi.x, lo.x);
+            split2(v[2], v[3], hi.y, lo.y);
+            split2(v[4], v[5], hi.z, lo.z);
+            split2(v[6], v[7], hi.w, lo.w);
+            const int off = (row >> 3) * gs + kc * 128 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(tc_b + off) = hi;
+            *reinterpret_cast<uint4*>(tc_b + tl.b_part + off) = lo;
+          }
+          __syncthreads();
+          if (tid < nbq) {
+            float cm2 = 0.f;
+            for (int j = 0; j < k; ++j) cm2 = fmaxf(cm2, tc_csq[tid * NPAD + j]);
+            const float cm = __fmul_rn(__fsqrt_rn(cm2), 1.0001f);
+            // |score_tc - score_fp32| <= 2^-13 |x| |c| + 2^-22 |c|^2 (3x the analytic bound: dropped lo*lo terms 3 * 2^-18,
+            // tensor-core accumulation, the fmaf chain's own rounding); ambiguous when the gap is within twice that
+            tc_thr[2 * tid] = __fmul_rn(cm, 0x1p-12f);
+            tc_thr[2 * tid + 1] = __fmul_rn(__fmul_rn(cm, cm), 0x1p-21f);
+          }
+          fence_proxy_async();
+          __syncthreads();
+        }
+        if (item + 1 < it1 && tid == 0) issue_load((item + 1) % tiles, tc_seq + 1);
+        const int i = tile * 256 + tid;
+        // previous labels / accounted clusters: fetched before the MMA wait so that their latency hides behind it
+        int lprev[8], aprev[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          lprev[q] = 0; aprev[q] = 255;
+          if (q < nbq && i < n) {
+            const size_t o = (size_t)s_batch_r[q] * ld + i;
+            lprev[q] = ws.labels[o];
+            if (mode == 0) aprev[q] = ws.acct[o];
+          }
+        }
+        const float xnorm = (i < n) ? ws.xn[i] : 0.f;
+        if (tid == 0) { s_nmoved = 0; s_namb = 0; s_chg = 0; }
+        // ---- MMAs of the item (warp 0, one elected lane)
+        if (warp == 0) {
+          const unsigned st = tc_seq & 1u;
+          mbar_wait(&s_afull[st], (tc_seq >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(tc_a + (size_t)st * tl.a_stage);
+          const uint32_t idesc = make_idesc(128, nbq * NPAD);
+          const uint64_t b_hi = make_desc(smem_u32(tc_b), 128, gs), b_lo = make_desc(smem_u32(tc_b + tl.b_part), 128, gs);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t ah = abase + (uint32_t)h * (128 * KP * 4);
+            const uint64_t a_hi = make_desc(ah, 128, gs), a_lo = make_desc(ah + 128 * KP * 2, 128, gs);
+            const uint32_t d = tmem + (uint32_t)h * 128u;
+            for (int kk = 0; kk < KP / 16; ++kk) {
+              const uint64_t ko = (uint64_t)((kk * 256) >> 4);
+              umma_bf16_e(el, d, a_hi + ko, b_hi + ko, idesc, kk > 0 ? 1u : 0u);
+              umma_bf16_e(el, d, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_bf16_e(el, d, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+          }
+          umma_commit_e(el, &s_mma);
+        }
+        __syncthreads();                                                    // the counters are reset before anyone appends
+        mbar_wait(&s_mma, tc_seq & 1u);
+        tc_fence_after();
+        // ---- scores -> best / second best per restart; ambiguous (point, restart) pairs go to the exact list
+        for (int q = 0; q < nbq; ++q) {
+          float best = 3.4e38f, second = 3.4e38f;
+          int bl = 0;
+          const float* cs = tc_csq + q * NPAD;
+          for (int c0 = 0; c0 < NPAD; c0 += 16) {
+            uint32_t d[16];
+            tmem_ld16_issue(t_row + (uint32_t)(q * NPAD + c0), d);
+            tmem_ld16_wait(d);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float v = __fmaf_rn(-2.f, __uint_as_float(d[u]), cs[c0 + u]);
+              if (v < best) { second = best; best = v; bl = c0 + u; }
+              else if (v < second) second = v;
+            }
+          }
+          tc_lab[q * 256 + tid] = (unsigned char)bl;
+          const bool amb = (i < n) && (k > 1) && !(__fsub_rn(second, best) > __fmaf_rn(tc_thr[2 * q], xnorm, tc_thr[2 * q + 1]));
+          const unsigned bal = __ballot_sync(0xffffffffu, amb);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(&s_namb, (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (amb) tc_amb[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(tid | (q << 8));
+          }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- exact path for the ambiguous pairs: the oracle's fmaf chain, strict <, first index wins
+        for (int e = tid; e < (int)s_namb; e += kLloydThreads) {
+          const int ent = tc_amb[e], pt = ent & 255, q = ent >> 8;
+          const int ip = tile * 256 + pt;
+          float x[CP];
+#pragma unroll
+          for (int f = 0; f < CP; ++f) x[f] = (f < C) ? Xc[(size_t)f * ld + ip] : 0.f;
+          const float* cq = tc_cent + (size_t)q * k * CP;
+          float bv = 0.f;
+          int bl = 0;
+          for (int j = 0; j < k; ++j) {
+            const float* c = cq + j * CP;
+            float dot = 0.f;
+#pragma unroll
+            for (int f = 0; f < CP; ++f) dot = __fmaf_rn(x[f], c[f], dot);
+            const float v = __fmaf_rn(-2.f, dot, tc_csq[q * NPAD + j]);
+            if (j == 0 || v < bv) { bv = v; bl = j; }
+          }
+          tc_lab[q * 256 + pt] = (unsigned char)bl;
+        }
+        __syncthreads();
+        // ---- labels, accounted clusters, list of moved points
+        for (int q = 0; q < nbq; ++q) {
+          const int l = tc_lab[q * 256 + tid];
+          bool moved = false, changed = false;
+          if (i < n) {
+            const size_t o = (size_t)s_batch_r[q] * ld + i;
+            if (mode == 0) {
+              moved = (l != aprev[q]);
+              if (moved) ws.acct[o] = (unsigned char)l;
+            }
+            if (l != lprev[q]) { ws.labels[o] = (unsigned char)l; changed = true; }
+          }
+          if (__any_sync(0xffffffffu, changed) && lane == 0) atomicOr(&s_chg, 1u << q);
+          if (mode == 0) {
+            const unsigned bal = __ballot_sync(0xffffffffu, moved);
+            if (bal) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&s_nmoved, __popc(bal));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (moved) tc_moved[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)tid | ((unsigned)aprev[q] << 8) | ((unsigned)l << 16) | ((unsigned)q << 24);
+            }
+          }
+        }
+        __syncthreads();
+        if (mode == 0) {
+          if (tid < nbq && ((s_chg >> tid) & 1u)) ws.changed[s_batch_r[tid]] = 1;
+          const int nm = s_nmoved;
+          for (int idx = tid; idx < nm * C; idx += kLloydThreads) {
+            const int e = idx / C, f = idx - e * C;
+            const unsigned ent = tc_moved[e];
+            const int pt = ent & 0xff, a = (ent >> 8) & 0xff, l = (ent >> 16) & 0xff, r = s_batch_r[ent >> 24];
+            long long* gsum = ws.sums + (size_t)r * k * C;
+            int* gcnt = ws.cnt + (size_t)r * k;
+            const long long qv = to_fixed(Xc[(size_t)f * ld + tile * 256 + pt], sc.p_x);
+            if (a != 255) atomicAdd((unsigned long long*)(gsum + a * C + f), (unsigned long long)(-qv));
+            atomicAdd((unsigned long long*)(gsum + l * C + f), (unsigned long long)qv);
+            if (f == 0) {
+              if (a != 255) atomicSub(gcnt + a, 1);
+              atomicAdd(gcnt + l, 1);
+            }
+          }
+        }
+        ++tc_seq;
+        __syncthreads();                                                    // lists / labels of the item are consumed
+      }
+    }
   };
 
   auto rebuild_active = [&](int want_mode) {
@@ -1182,7 +1497,7 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
     rebuild_active(0);
     if (s_nactive == 0) break;
     ++total_iters;
-    run_estep(0);
+    if constexpr (TC) run_estep_tc(0); else run_estep(0);
     lap(t_e);
     grid_barrier(ws.barrier, epoch);
     lap(t_b1);
@@ -1198,7 +1513,7 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
 
   // ---- E-step re-run for restarts that did not converge strictly
   rebuild_active(1);
-  if (s_nactive > 0) run_estep(1);
+  if (s_nactive > 0) { if constexpr (TC) run_estep_tc(1); else run_estep(1); }
   grid_barrier(ws.barrier, epoch);
 
   // ---- inertia of every restart (direct-form distances, exact fixed-point sum)
@@ -1279,6 +1594,11 @@ __global__ void __launch_bounds__(kLloydThreads, PPT == 2 ? 2 : 1) km_lloyd_kern
       for (int q = 0; q < 6; ++q) prm.info[10 + q] = (int)(ws.seed_prof[q] / 1000);   // seeding kernel: search, pass 1, pass 2, barriers (us); search segments, rounds
     }
   }
+  if constexpr (TC) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+  }
 }
 
 
@@ -1299,7 +1619,7 @@ constexpr int kFlowSlice = kFlowHalf * kFlowPPT;   // 512 points per CTA at most
 
 template <int CP>
 __global__ void __launch_bounds__(kLloydThreads, 1) km_lloyd_flow_kernel(const LloydParams prm, int batch) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = *prm.n_ptr;
   const int C = prm.C, k = prm.k, R = prm.R, ld = prm.ld;
   const KmWs& ws = prm.ws;
@@ -1627,6 +1947,10 @@ size_t lloyd_smem_bytes(int k, int C, int CP) {
   size_t fl = (size_t)3 * k * CP + (k + 3) / 4 * 4;
   return fl * 4 + (size_t)kMaxTile * 4 + 16;
 }
+size_t lloyd_tc_smem_bytes(int k, int C, int CP) {
+  const size_t base = (((size_t)(k * CP + (k + 3) / 4 * 4) * 4 + 127) / 128) * 128;
+  return base + km_tc_layout(C, CP, k).total + 128;
+}
 
 template <int CP, bool RES>
 int launch_seed_v(const int* n_ptr, int ld, int C, int k, int L, int R, const double* uniforms, const KmWs& ws, int num_sms, cudaStream_t stream,
@@ -1672,10 +1996,31 @@ int launch_seed(const int* n_ptr, int ld, int C, int k, int L, int R, const doub
   return launch_seed_v<CP, false>(n_ptr, ld, C, k, L, R, uniforms, ws, num_sms, stream, &launched);
 }
 
+// Tensor-core E-step (C <= 32, k <= 128): two CTAs per SM, 256 tensor-memory columns each.
+template <int CP>
+int launch_lloyd_tc(const LloydParams& prm, int num_sms, cudaStream_t stream) {
+  if constexpr (CP <= 32) {
+    const size_t smem = lloyd_tc_smem_bytes(prm.k, prm.C, CP);
+    const void* fn = (const void*)km_lloyd_kernel<CP, 2, true>;
+    ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLloydThreads, smem));
+    ISA_CHECK_ARG(occ >= 1, "kmeans: tensor-core Lloyd kernel does not fit on an SM (smem %zu)", smem);
+    if (occ > 2) occ = 2;
+    km_prep_tc_kernel<<<(km_tc_halftiles(prm.ld) * 128 + 255) / 256, 256, 0, stream>>>(prm.n_ptr, prm.ld, prm.C, km_tc_kp(prm.C), prm.ws);
+    ISA_CUDA(cudaGetLastError());
+    void* args[] = {(void*)&prm};
+    ISA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms * occ), dim3(kLloydThreads), args, smem, stream));
+    return ISA_OK;
+  } else {
+    return ISA_ERR_UNSUPPORTED;
+  }
+}
+
 template <int CP, int PPT>
 int launch_lloyd_ppt(const LloydParams& prm, int num_sms, cudaStream_t stream) {
   const size_t smem = lloyd_smem_bytes(prm.k, prm.C, CP);
-  const void* fn = (const void*)km_lloyd_kernel<CP, PPT>;
+  const void* fn = (const void*)km_lloyd_kernel<CP, PPT, false>;
   if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLloydThreads, smem));
@@ -1726,6 +2071,9 @@ int launch_lloyd(const LloydParams& prm, int num_sms, cudaStream_t stream) {
     rc = launch_lloyd_flow<CP>(prm, num_sms, di.max_smem_optin, stream, &launched);
     if (rc || launched) return rc;
   }
+  // default: the tensor-core E-step (ISA_KM_FFMA=1 keeps the packed-FP32 kernel: the measured alternative and the
+  // path for C > 32 or k > 128)
+  if (CP <= 32 && km_tc_ok(prm.C, prm.k) && !getenv("ISA_KM_FFMA")) return launch_lloyd_tc<CP>(prm, num_sms, stream);
   int ppt = (CP <= 32) ? 2 : 4;   // ISA_KM_PPT=4 with CP <= 32 selects the scalar four-point E-step (estep_tile4): same speed
   const char* e = getenv("ISA_KM_PPT");
   if (e && (e[0] == '2' || e[0] == '4')) ppt = e[0] - '0';
