@@ -228,6 +228,23 @@ int isa_row_dot(const float* a, const float* b, int rows, int HW, int b_rows_div
                 size_t workspace_bytes, isa_stream_t stream);
 int isa_row_affine(const float* x, const float* g, const float* c, int rows, int HW, float* y, isa_stream_t stream);
 
+/* ------------------------------------------------------------------ masked batch norm
+ * /root/reference/code/lib/archs/modules/utils.py:568-591 maskBN.forward in training mode (HardAttentionLayer's
+ * normalisation over the foreground, :645): mm[b] = sum of the mask over all channels and pixels + 1,
+ *   mean[c] = (1/B) sum_b (sum_p x m) / mm[b],  var[c] = (1/B) sum_b (sum_p (x - mean[c])^2 m) / mm[b],
+ *   y = (x - mean) / sqrt(var + eps) * weight + bias  (weight / bias NULL: 1 / 0).
+ * x, y [B][C][HW] f32; mask [B][mask_channels][HW] f32 with mask_channels 1 (shared by the channels) or C.
+ * stats [2*C + B*mask_channels]: mean, var (what the running averages are updated from) and the mask sums the
+ * backward call needs.  Backward differentiates through mean and var like the reference's autograd graph:
+ * dx [B][C][HW], dweight / dbias [C] (NULL: skipped); no gradient for the mask.  Deterministic two-stage sums. */
+size_t isa_mask_bn_workspace_bytes(int B, int C, int HW);
+int isa_mask_bn_fwd(const float* x, const float* mask, int mask_channels, int B, int C, int HW, const float* weight,
+                    const float* bias, float eps, float* y, float* stats, void* workspace, size_t workspace_bytes,
+                    isa_stream_t stream);
+int isa_mask_bn_bwd(const float* x, const float* mask, int mask_channels, const float* dy, const float* stats,
+                    const float* weight, float eps, int B, int C, int HW, float* dx, float* dweight, float* dbias,
+                    void* workspace, size_t workspace_bytes, isa_stream_t stream);
+
 /* ------------------------------------------------------------------ single-query readout
  * /root/reference/code/lib/archs/modules/utils.py:59-69 Decoder.forward: sigmoid(bmm(q (b,1,C), enc (b,C,HW))).
  * q [B][C], enc [B][C][HW], out [B][HW].  Backward writes dz = dout * out * (1 - out) [B][HW] and, if denc is

@@ -85,6 +85,11 @@ SIGNATURES = {
     "isa_row_dot_workspace_bytes": (c_size_t, [c_int, c_int]),
     "isa_row_dot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_row_affine": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "isa_mask_bn_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "isa_mask_bn_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isa_mask_bn_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "isa_readout_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "isa_readout_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "isa_local_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -141,6 +146,7 @@ KERNELS_PER_CALL = {
     "isa_attention_fwd": 2, "isa_attention_probs": 1, "isa_attention_bwd": 3,
     "isa_gru_scan_fwd": 1, "isa_gru_scan_bwd": 1,
     "isa_masked_softmax_hw_fwd": 2, "isa_masked_softmax_hw_bwd": 3, "isa_row_dot": 2, "isa_row_affine": 1,
+    "isa_mask_bn_fwd": 5, "isa_mask_bn_bwd": 2,
     "isa_readout_fwd": 1, "isa_readout_bwd": 1, "isa_local_attention_fwd": 1, "isa_local_attention_bwd": 2,
     "isa_bias_act_fwd": 1, "isa_bias_act_bwd": 2, "isa_add_layernorm_fwd": 1, "isa_add_layernorm_bwd": 2,
     "isa_pixel_heads_fwd": 1, "isa_pixel_heads_bwd": 1, "isa_pixel_heads_wgrad": 2,

@@ -809,6 +809,7 @@ struct LloydParams {
   double* inertia_out;  // [R]
   int* n_iter_out;      // [R]
   int* info;            // [16] status, best restart, n, total Lloyd iterations, then CTA 0's phase profile in us
+  int priv;             // packed-FP32 kernel: accumulate the moved points of a CTA in shared memory (k*C int64 + k int)
 };
 
 typedef unsigned long long km_u64;
@@ -1117,6 +1118,8 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
   float* s_csq = s_cent + k * CP;                                           // [k]
   float* s_cdup = s_csq + (k + 3) / 4 * 4;                                  // [k][CP] x {c, c} (16 B aligned); FFMA E-step only
   unsigned* s_moved = reinterpret_cast<unsigned*>(s_cdup + (TC ? 0 : (size_t)2 * k * CP));  // [kTile] (point in tile | old << 12 | new << 20)
+  long long* s_acc = reinterpret_cast<long long*>(s_moved + kMaxTile);          // [k][C] privatised centre-sum deltas (prm.priv)
+  int* s_acnt = reinterpret_cast<int*>(s_acc + (size_t)k * C);                  // [k] count deltas
   // tensor-core E-step: its own region behind the update's centres
   unsigned char* tc_base = smem_raw + (((size_t)(k * CP + (k + 3) / 4 * 4) * 4 + 127) / 128) * 128;
   const TcLayout tl = km_tc_layout(C, CP, k);
@@ -1153,9 +1156,28 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
     // balanced contiguous ranges (sizes differ by at most one item; ceil-sized ranges left up to half the CTAs idle)
     const int it0 = (int)((long long)blockIdx.x * total / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
     int cur = -1;
+    bool acc_dirty = false;
+    // privatised M-step (prm.priv): the exact fixed-point deltas of this CTA's moved points are summed in shared memory and
+    // reach the global sums once per (CTA, restart) -- k*C reductions instead of 2*C per moved point
+    auto flush_acc = [&](int r) {
+      __syncthreads();
+      long long* gs = ws.sums + (size_t)r * k * C;
+      int* gcnt = ws.cnt + (size_t)r * k;
+      for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) {
+        const long long v = s_acc[idx];
+        if (v) { atomicAdd((unsigned long long*)(gs + idx), (unsigned long long)v); s_acc[idx] = 0; }
+      }
+      for (int j = threadIdx.x; j < k; j += kLloydThreads) {
+        const int c = s_acnt[j];
+        if (c) { atomicAdd(gcnt + j, c); s_acnt[j] = 0; }
+      }
+      __syncthreads();
+      acc_dirty = false;
+    };
     for (int item = it0; item < it1; ++item) {
       const int r = s_active[item / tiles], tile = item % tiles;
       if (r != cur) {
+        if (acc_dirty) flush_acc(cur);
         __syncthreads();
         load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP, s_cdup);
         cur = r;
@@ -1206,6 +1228,21 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
         const int nm = s_nmoved;
         long long* gs = ws.sums + (size_t)r * k * C;
         int* gcnt = ws.cnt + (size_t)r * k;
+        if (prm.priv && nm >= 8) {
+          acc_dirty = true;
+          for (int idx = threadIdx.x; idx < nm * C; idx += kLloydThreads) {
+            const int e = idx / C, f = idx - e * C;
+            const unsigned ent = s_moved[e];
+            const int li = ent & 0xfff, a = (ent >> 12) & 0xff, l = (ent >> 20) & 0xff;
+            const long long q = to_fixed(Xc[(size_t)f * ld + tile * kTile + li], sc.p_x);
+            if (a != 255) smem_add64(s_acc + a * C + f, -q);
+            smem_add64(s_acc + l * C + f, q);
+            if (f == 0) {
+              if (a != 255) atomicSub(s_acnt + a, 1);
+              atomicAdd(s_acnt + l, 1);
+            }
+          }
+        } else
         for (int idx = threadIdx.x; idx < nm * C; idx += kLloydThreads) {
           const int e = idx / C, f = idx - e * C;
           const unsigned ent = s_moved[e];
@@ -1220,6 +1257,7 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
         }
       }
     }
+    if (acc_dirty) flush_acc(cur);
    }
   };
 
@@ -1481,6 +1519,10 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
     __syncthreads();
   };
 
+  if (!TC && prm.priv) {
+    for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) s_acc[idx] = 0;
+    for (int j = threadIdx.x; j < k; j += kLloydThreads) s_acnt[j] = 0;
+  }
   // labels / acct start as "none" (255)
   for (size_t idx = (size_t)blockIdx.x * kLloydThreads + threadIdx.x; idx < (size_t)R * ld; idx += (size_t)gridDim.x * kLloydThreads) {
     ws.labels[idx] = 255;
@@ -2018,8 +2060,14 @@ int launch_lloyd_tc(const LloydParams& prm, int num_sms, cudaStream_t stream) {
 }
 
 template <int CP, int PPT>
-int launch_lloyd_ppt(const LloydParams& prm, int num_sms, cudaStream_t stream) {
-  const size_t smem = lloyd_smem_bytes(prm.k, prm.C, CP);
+int launch_lloyd_ppt(const LloydParams& prm_in, int num_sms, cudaStream_t stream) {
+  LloydParams prm = prm_in;
+  size_t smem = lloyd_smem_bytes(prm.k, prm.C, CP);
+  const size_t extra = (size_t)prm.k * prm.C * 8 + (size_t)(prm.k + 3) / 4 * 4 * 4 + 16;
+  // Measured on B200 (49 k points, C = 24, k = 16, 35 restarts): E-phase 5.99 ms with the shared-memory accumulation against
+  // 6.06 ms with direct RED.64s -- the reductions are not what the E-phase waits for; kept behind ISA_KM_PRIV=1.
+  prm.priv = (getenv("ISA_KM_PRIV") && (smem + extra) * 2 <= 200 * 1024) ? 1 : 0;   // must not cost the second CTA per SM
+  if (prm.priv) smem += extra;
   const void* fn = (const void*)km_lloyd_kernel<CP, PPT, false>;
   if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -2073,7 +2121,12 @@ int launch_lloyd(const LloydParams& prm, int num_sms, cudaStream_t stream) {
   }
   // default: the tensor-core E-step (ISA_KM_FFMA=1 keeps the packed-FP32 kernel: the measured alternative and the
   // path for C > 32 or k > 128)
-  if (CP <= 32 && km_tc_ok(prm.C, prm.k) && !getenv("ISA_KM_FFMA")) return launch_lloyd_tc<CP>(prm, num_sms, stream);
+  // Measured on B200 (tools/bench_kmeans.py): k = 64, C = 32, 524 k points: 114 ms against 135 ms for the packed-FP32
+  // kernel (E-steps 60 / 80 ms); k = 16, C = 24: 10.3 against 8.9 ms (49 k points), 19.2 against 16.7 ms (131 k): with 16
+  // centres the per-item costs of the batch (operand conversion, MMA round trip, tensor-memory reads, the exact pass)
+  // outweigh the 384 FFMAs per point they replace.  Default: tensor cores from 33 centres on; ISA_KM_TC=1 / ISA_KM_FFMA=1 force.
+  const bool want_tc = getenv("ISA_KM_TC") ? true : (getenv("ISA_KM_FFMA") ? false : prm.k > 32);
+  if (CP <= 32 && km_tc_ok(prm.C, prm.k) && want_tc) return launch_lloyd_tc<CP>(prm, num_sms, stream);
   int ppt = (CP <= 32) ? 2 : 4;   // ISA_KM_PPT=4 with CP <= 32 selects the scalar four-point E-step (estep_tile4): same speed
   const char* e = getenv("ISA_KM_PPT");
   if (e && (e[0] == '2' || e[0] == '4')) ppt = e[0] - '0';
@@ -2138,7 +2191,7 @@ int isa_kmeans_fit(const float* X, const int* n_ptr, int ld, int C, int k, int n
   LloydParams prm;
   prm.n_ptr = n_ptr; prm.ld = ld; prm.C = C; prm.k = k; prm.R = n_init; prm.max_iter = max_iter; prm.tol_rel = tol_rel;
   prm.ws = ws; prm.labels_out = labels_out; prm.centers_out = centers_out; prm.inertia_out = inertia_out;
-  prm.n_iter_out = n_iter_out; prm.info = info;
+  prm.n_iter_out = n_iter_out; prm.info = info; prm.priv = 0;
   switch (CP) {
     case 8: rc = launch_lloyd<8>(prm, di.num_sms, stream); break;
     case 16: rc = launch_lloyd<16>(prm, di.num_sms, stream); break;

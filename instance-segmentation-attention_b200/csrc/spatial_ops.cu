@@ -257,6 +257,130 @@ __global__ void __launch_bounds__(kThreads) readout_bwd_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------ masked batch norm (utils.py:529-591 maskBN, training mode)
+//   mm[b]   = sum over ALL channels and pixels of the mask + 1            (utils.py:574)
+//   mean[c] = (1/B) sum_b (sum_p x m) / mm[b]          var[c] = (1/B) sum_b (sum_p (x - mean[c])^2 m) / mm[b]
+//   y       = (x - mean) / sqrt(var + eps) * weight + bias                (every pixel, masked or not)
+// and the gradient flows through mean AND var like the reference's autograd graph does.  All sums are two-stage and
+// folded in a fixed order (per-chunk block sums -> loops over chunks and images): deterministic.
+// msum [B][MC] = per-row mask sums (MC = 1: one mask plane shared by the channels, MC = C: one per channel).
+__device__ __forceinline__ float mbn_mask_mean(const float* __restrict__ msum, int b, int C, int MC) {
+  float t = 0.f;
+  if (MC == 1) t = (float)C * msum[b];
+  else for (int c = 0; c < C; ++c) t += msum[(size_t)b * MC + c];
+  return t + 1.f;
+}
+// fold of a [B][C][nc] partial array over chunks and images for channel c, each image weighted by 1 / (B mm[b])
+__device__ __forceinline__ float mbn_fold(const float* __restrict__ part, const float* __restrict__ msum, int B, int C, int MC, int nc, int c,
+                                          bool weighted) {
+  float tot = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float r = 0.f;
+    const float* pr = part + ((size_t)b * C + c) * nc;
+    for (int i = 0; i < nc; ++i) r += pr[i];
+    tot += weighted ? r / (mbn_mask_mean(msum, b, C, MC) * (float)B) : r;
+  }
+  return tot;
+}
+
+// part2[row][chunk] = sum_p (x - mean[c])^2 m
+__global__ void __launch_bounds__(kThreads) mbn_var_part_kernel(const float* __restrict__ x, const float* __restrict__ mask, int MC,
+                                                                const float* __restrict__ part1, const float* __restrict__ msum, int B, int C,
+                                                                int HW, int nc, float* __restrict__ part2) {
+  __shared__ float s_red[kThreads / 32];
+  __shared__ float s_mean;
+  const int row = blockIdx.y, chunk = blockIdx.x, b = row / C, c = row - b * C;
+  if (threadIdx.x == 0) s_mean = mbn_fold(part1, msum, B, C, MC, nc, c, true);
+  __syncthreads();
+  const float mean = s_mean;
+  const float* xr = x + (size_t)row * HW;
+  const float* mr = mask + ((size_t)b * MC + (MC == 1 ? 0 : c)) * HW;
+  const int p0 = chunk * kChunk, p1 = min(HW, p0 + kChunk);
+  float acc = 0.f;
+  for (int p = p0 + threadIdx.x; p < p1; p += kThreads) {
+    const float d = xr[p] - mean;
+    acc = fmaf(d * d, mr[p], acc);
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part2[(size_t)row * nc + chunk] = acc;
+}
+
+// y = (x - mean) * rstd * w + bias; the first CTA of every channel also records (mean, var)
+__global__ void __launch_bounds__(kThreads) mbn_norm_kernel(const float* __restrict__ x, const float* __restrict__ part1, const float* __restrict__ part2,
+                                                            const float* __restrict__ msum, const float* __restrict__ weight,
+                                                            const float* __restrict__ bias, float eps, int B, int C, int MC, int HW, int nc,
+                                                            float* __restrict__ y, float* __restrict__ stats) {
+  __shared__ float s_mv[2];
+  const int row = blockIdx.y, chunk = blockIdx.x, b = row / C, c = row - b * C;
+  if (threadIdx.x == 0) {
+    s_mv[0] = mbn_fold(part1, msum, B, C, MC, nc, c, true);
+    s_mv[1] = mbn_fold(part2, msum, B, C, MC, nc, c, true);
+    if (b == 0 && chunk == 0) { stats[c] = s_mv[0]; stats[C + c] = s_mv[1]; }
+  }
+  __syncthreads();
+  const float mean = s_mv[0], rstd = 1.f / sqrtf(s_mv[1] + eps);
+  const float g = (weight ? weight[c] : 1.f) * rstd, sh = bias ? bias[c] : 0.f;
+  const int p0 = chunk * kChunk, p1 = min(HW, p0 + kChunk);
+  const float* xr = x + (size_t)row * HW;
+  float* yr = y + (size_t)row * HW;
+  for (int p = p0 + threadIdx.x; p < p1; p += kThreads) yr[p] = fmaf(xr[p] - mean, g, sh);
+}
+
+// g1[row][chunk] = sum_p dy, g2[row][chunk] = sum_p dy (x - mean[c])
+__global__ void __launch_bounds__(kThreads) mbn_bwd_part_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                                                                int C, int HW, int nc, float* __restrict__ g1, float* __restrict__ g2) {
+  __shared__ float s_red[kThreads / 32];
+  const int row = blockIdx.y, chunk = blockIdx.x, c = row % C;
+  const float mean = stats[c];
+  const float* xr = x + (size_t)row * HW;
+  const float* gr = dy + (size_t)row * HW;
+  const int p0 = chunk * kChunk, p1 = min(HW, p0 + kChunk);
+  float a1 = 0.f, a2 = 0.f;
+  for (int p = p0 + threadIdx.x; p < p1; p += kThreads) {
+    const float g = gr[p];
+    a1 += g;
+    a2 = fmaf(g, xr[p] - mean, a2);
+  }
+  a1 = block_sum(a1, s_red);
+  __syncthreads();
+  a2 = block_sum(a2, s_red);
+  if (threadIdx.x == 0) { g1[(size_t)row * nc + chunk] = a1; g2[(size_t)row * nc + chunk] = a2; }
+}
+
+// dx = dy r w + m / (B mm[b]) * (dL/dmean + 2 dL/dvar (x - mean));  dweight = r sum dy (x - mean), dbias = sum dy
+__global__ void __launch_bounds__(kThreads) mbn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ mask, int MC,
+                                                              const float* __restrict__ dy, const float* __restrict__ stats,
+                                                              const float* __restrict__ msum, const float* __restrict__ weight, float eps,
+                                                              const float* __restrict__ g1, const float* __restrict__ g2, int B, int C, int HW, int nc,
+                                                              float* __restrict__ dx, float* __restrict__ dweight, float* __restrict__ dbias) {
+  __shared__ float s_v[4];
+  const int row = blockIdx.y, chunk = blockIdx.x, b = row / C, c = row - b * C;
+  if (threadIdx.x == 0) {
+    const float mean = stats[c], rstd = 1.f / sqrtf(stats[C + c] + eps), w = weight ? weight[c] : 1.f;
+    const float G1 = mbn_fold(g1, msum, B, C, MC, nc, c, false), G2 = mbn_fold(g2, msum, B, C, MC, nc, c, false);
+    // A = sum_b (sum_p m) / (B mm[b]): the weights of the masked mean do not add up to one (the "+ 1", and mm counts
+    // every channel), so d var / d mean = -2 mean_of_(x - mean) = -2 mean (1 - A) does not vanish
+    float A = 0.f;
+    for (int bb = 0; bb < B; ++bb) A += msum[(size_t)bb * MC + (MC == 1 ? 0 : c)] / (mbn_mask_mean(msum, bb, C, MC) * (float)B);
+    const float dvar = -0.5f * w * rstd * rstd * rstd * G2;
+    const float dmean = -rstd * w * G1 + dvar * (-2.f * mean * (1.f - A));
+    s_v[0] = rstd * w; s_v[1] = dmean; s_v[2] = 2.f * dvar; s_v[3] = mean;
+    if (b == 0 && chunk == 0) {
+      if (dweight) dweight[c] = rstd * G2;
+      if (dbias) dbias[c] = G1;
+    }
+  }
+  __syncthreads();
+  const float rw = s_v[0], dmean = s_v[1], dvar2 = s_v[2], mean = s_v[3];
+  const float ab = 1.f / (mbn_mask_mean(msum, b, C, MC) * (float)B);
+  const float* xr = x + (size_t)row * HW;
+  const float* gr = dy + (size_t)row * HW;
+  const float* mr = mask + ((size_t)b * MC + (MC == 1 ? 0 : c)) * HW;
+  float* dr = dx + (size_t)row * HW;
+  const int p0 = chunk * kChunk, p1 = min(HW, p0 + kChunk);
+  for (int p = p0 + threadIdx.x; p < p1; p += kThreads) dr[p] = fmaf(gr[p], rw, ab * mr[p] * fmaf(dvar2, xr[p] - mean, dmean));
+}
+
 int chunks_of(int HW) { return (HW + kChunk - 1) / kChunk; }
 
 }  // namespace
@@ -325,6 +449,53 @@ int isa_row_affine(const float* x, const float* g, const float* c, int rows, int
   ISA_CHECK_ARG(x && g && y, "row_affine: null pointer");
   ISA_CHECK_ARG(rows > 0 && rows <= 65535 && HW > 0, "row_affine: bad sizes (rows=%d HW=%d)", rows, HW);
   row_affine_kernel<<<dim3(chunks_of(HW), rows), kThreads, 0, stream>>>(x, g, c, HW, y);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+size_t isa_mask_bn_workspace_bytes(int B, int C, int HW) {
+  return 4 * isa_align_up((size_t)B * C * chunks_of(HW) * sizeof(float), 256);
+}
+
+int isa_mask_bn_fwd(const float* x, const float* mask, int mask_channels, int B, int C, int HW, const float* weight, const float* bias, float eps,
+                    float* y, float* stats, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ISA_CHECK_ARG(x && mask && y && stats && workspace, "mask_bn_fwd: null pointer");
+  ISA_CHECK_ARG(B > 0 && C > 0 && HW > 0 && (long long)B * C <= 65535, "mask_bn_fwd: bad sizes (B=%d C=%d HW=%d)", B, C, HW);
+  ISA_CHECK_ARG(mask_channels == 1 || mask_channels == C, "mask_bn_fwd: the mask has 1 or C channels (got %d)", mask_channels);
+  ISA_CHECK_ARG(workspace_bytes >= isa_mask_bn_workspace_bytes(B, C, HW), "mask_bn_fwd: workspace too small");
+  const int rows = B * C, nc = chunks_of(HW), MC = mask_channels;
+  const size_t stride = isa_align_up((size_t)rows * nc * sizeof(float), 256) / sizeof(float);
+  float* part1 = reinterpret_cast<float*>(workspace);
+  float* part2 = part1 + stride;
+  float* pm = part2 + stride;
+  float* msum = stats + 2 * C;                                           // [B][MC], kept for the backward call
+  rowdot_part_kernel<<<dim3(nc, rows), kThreads, 0, stream>>>(x, mask, MC == 1 ? C : 1, HW, nc, part1);
+  ISA_CUDA(cudaGetLastError());
+  rowdot_part_kernel<<<dim3(nc, B * MC), kThreads, 0, stream>>>(mask, nullptr, 1, HW, nc, pm);
+  ISA_CUDA(cudaGetLastError());
+  rowdot_final_kernel<<<(B * MC + 127) / 128, 128, 0, stream>>>(pm, B * MC, nc, msum);
+  ISA_CUDA(cudaGetLastError());
+  mbn_var_part_kernel<<<dim3(nc, rows), kThreads, 0, stream>>>(x, mask, MC, part1, msum, B, C, HW, nc, part2);
+  ISA_CUDA(cudaGetLastError());
+  mbn_norm_kernel<<<dim3(nc, rows), kThreads, 0, stream>>>(x, part1, part2, msum, weight, bias, eps, B, C, MC, HW, nc, y, stats);
+  ISA_CUDA(cudaGetLastError());
+  return ISA_OK;
+}
+
+int isa_mask_bn_bwd(const float* x, const float* mask, int mask_channels, const float* dy, const float* stats, const float* weight, float eps,
+                    int B, int C, int HW, float* dx, float* dweight, float* dbias, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ISA_CHECK_ARG(x && mask && dy && stats && dx && workspace, "mask_bn_bwd: null pointer");
+  ISA_CHECK_ARG(B > 0 && C > 0 && HW > 0 && (long long)B * C <= 65535, "mask_bn_bwd: bad sizes (B=%d C=%d HW=%d)", B, C, HW);
+  ISA_CHECK_ARG(mask_channels == 1 || mask_channels == C, "mask_bn_bwd: the mask has 1 or C channels (got %d)", mask_channels);
+  ISA_CHECK_ARG(workspace_bytes >= isa_mask_bn_workspace_bytes(B, C, HW), "mask_bn_bwd: workspace too small");
+  const int rows = B * C, nc = chunks_of(HW), MC = mask_channels;
+  const size_t stride = isa_align_up((size_t)rows * nc * sizeof(float), 256) / sizeof(float);
+  float* g1 = reinterpret_cast<float*>(workspace);
+  float* g2 = g1 + stride;
+  const float* msum = stats + 2 * C;
+  mbn_bwd_part_kernel<<<dim3(nc, rows), kThreads, 0, stream>>>(x, dy, stats, C, HW, nc, g1, g2);
+  ISA_CUDA(cudaGetLastError());
+  mbn_bwd_dx_kernel<<<dim3(nc, rows), kThreads, 0, stream>>>(x, mask, MC, dy, stats, msum, weight, eps, g1, g2, B, C, HW, nc, dx, dweight, dbias);
   ISA_CUDA(cudaGetLastError());
   return ISA_OK;
 }

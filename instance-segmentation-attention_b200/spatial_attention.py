@@ -352,6 +352,50 @@ class SpatialAttentionLayer(nn.Module):
         return beta
 
 
+class _MaskBN(torch.autograd.Function):
+    """Training-mode maskBN (utils.py:568-591) on the device: masked statistics, normalisation and the gradient through
+    mean and var, as deterministic two-stage reductions (csrc/spatial_ops.cu mbn_*).  Returns (y, mean, var)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, weight, bias, eps):
+        lib = _lib.load()
+        _lib.require_cuda(x, "input")
+        x = _f32c(x)
+        b, c, h, w = x.shape
+        mask = _f32c(mask.to(torch.float32).reshape(b, -1, h * w))
+        mc = mask.shape[1]
+        y = torch.empty_like(x)
+        stats = torch.empty(2 * c + b * mc, device=x.device, dtype=torch.float32)
+        wsb = lib.isa_mask_bn_workspace_bytes(b, c, h * w)
+        ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+        wt = _f32c(weight) if weight is not None else None
+        bs = _f32c(bias) if bias is not None else None
+        rc = lib.isa_mask_bn_fwd(_lib.ptr(x), _lib.ptr(mask), mc, b, c, h * w, _lib.ptr(wt), _lib.ptr(bs), float(eps),
+                                 _lib.ptr(y), _lib.ptr(stats), _lib.ptr(ws), wsb, _lib.stream_ptr(x.device))
+        _lib.check(rc, "isa_mask_bn_fwd")
+        ctx.save_for_backward(x, mask, stats, wt)
+        ctx.meta = (b, c, h * w, mc, float(eps), weight is not None, bias is not None)
+        mean, var = stats[:c].clone(), stats[c:2 * c].clone()
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _dvar):
+        lib = _lib.load()
+        x, mask, stats, wt = ctx.saved_tensors
+        b, c, hw, mc, eps, has_w, has_b = ctx.meta
+        dy = _f32c(dy)
+        dx = torch.empty_like(x)
+        dw = torch.empty(c, device=x.device, dtype=torch.float32) if has_w else None
+        db = torch.empty(c, device=x.device, dtype=torch.float32) if has_b else None
+        wsb = lib.isa_mask_bn_workspace_bytes(b, c, hw)
+        ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+        rc = lib.isa_mask_bn_bwd(_lib.ptr(x), _lib.ptr(mask), mc, _lib.ptr(dy), _lib.ptr(stats), _lib.ptr(wt), eps, b, c, hw,
+                                 _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), wsb, _lib.stream_ptr(x.device))
+        _lib.check(rc, "isa_mask_bn_bwd")
+        return dx, None, dw, db, None
+
+
 class maskBN(nn.Module):
     """utils.py:529-591: batch statistics weighted by a (b,c,h,w) mask, per-image normaliser sum(mask) + 1.
     The running-average update keeps the reference's (reversed) momentum convention (utils.py:583-584)."""
@@ -396,19 +440,14 @@ class maskBN(nn.Module):
             self.num_batches_tracked += 1
             factor = 1.0 / self.num_batches_tracked.item() if self.momentum is None else self.momentum
         if self.training or not self.track_running_stats:
-            mask = mask.to(input.dtype).expand(b, c, h, w)
-            mask_mean = torch.sum(mask.reshape(b, -1), dim=1) + 1            # utils.py:574 (sums all c channels)
-            x2 = input.reshape(b, c, h * w)
-            m2 = mask.reshape(b, c, h * w)
-            mean = torch.mean(torch.sum(x2 * m2, dim=2) / mask_mean[:, None], dim=0)
-            var = torch.mean(torch.sum((x2 - mean[None, :, None]) ** 2 * m2, dim=2) / mask_mean[:, None], dim=0)
+            assert mask.shape[1] in (1, c), "maskBN: the mask has one channel or one per feature"
+            out, mean, var = _MaskBN.apply(input, mask, self.weight if self.affine else None,
+                                           self.bias if self.affine else None, self.eps)
             if self.track_running_stats:
-                with torch.no_grad():
+                with torch.no_grad():      # the reference's convention (utils.py:580-581): running * factor + (1 - factor) * batch
                     self.running_mean.copy_(self.running_mean * factor + (1 - factor) * mean)
                     self.running_var.copy_(self.running_var * factor + (1 - factor) * var)
-            w_ = self.weight.view(1, c, 1, 1) if self.affine else 1.0
-            b_ = self.bias.view(1, c, 1, 1) if self.affine else 0.0
-            return (input - mean.view(1, c, 1, 1)) / torch.pow(var.view(1, c, 1, 1) + self.eps, 0.5) * w_ + b_
+            return out
         w_ = self.weight.view(1, c, 1, 1) if self.affine else 1.0
         b_ = self.bias.view(1, c, 1, 1) if self.affine else 0.0
         return (input - self.running_mean.view(1, c, 1, 1)) / torch.pow(self.running_var.view(1, c, 1, 1) + self.eps, 0.5) * w_ + b_

@@ -217,3 +217,38 @@ def test_squeeze_excite_vs_oracle(cuda, b, c, h, w):
     assert _rel(xg.grad, xr.grad) < RTOL
     for q_, r_ in zip((m.fc[0].weight, m.fc[0].bias, m.fc[2].weight, m.fc[2].bias), p):
         assert _rel(q_.grad, r_.grad) < RTOL
+
+
+@pytest.mark.parametrize("b,c,h,w,per_channel_mask", [(4, 1, 64, 64, False), (3, 5, 33, 47, False), (2, 4, 40, 24, True), (16, 1, 256, 256, False)])
+def test_mask_bn_vs_oracle(cuda, b, c, h, w, per_channel_mask):
+    """maskBN's training branch (utils.py:573-586) as kernels: output, batch statistics / running averages, and the gradient
+    THROUGH the masked mean and variance (input, weight, bias) against the float64 autograd of the restated formula."""
+    from isa_b200.spatial_attention import maskBN
+    torch.manual_seed(7 * b + c)
+    m = maskBN(c).to(cuda).train()
+    x = torch.randn(b, c, h, w) * 1.7 + 0.6
+    mask = (torch.rand(b, c if per_channel_mask else 1, h, w) > 0.4).float()
+    mask[0] = 0                                                     # an image without foreground: mm = 1
+    wr = m.weight.detach().double().cpu().requires_grad_(True)
+    br = m.bias.detach().double().cpu().requires_grad_(True)
+    xr = x.double().requires_grad_(True)
+    yr = O.mask_bn_train_ref(xr, mask.double(), wr, br, m.eps)
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    xg = x.to(cuda).requires_grad_(True)
+    yg = m(xg, mask.to(cuda))
+    assert _rel(yg, yr) < RTOL
+    yg.backward(g.float().to(cuda))
+    assert _rel(xg.grad, xr.grad) < RTOL
+    assert _rel(m.weight.grad, wr.grad) < RTOL and _rel(m.bias.grad, br.grad) < RTOL
+    # running averages: the reference's convention running * momentum + (1 - momentum) * batch (utils.py:580-581)
+    mm = mask.double().expand(b, c, h, w).reshape(b, -1).sum(1) + 1
+    x2, m2 = x.double().reshape(b, c, -1), mask.double().expand(b, c, h, w).reshape(b, c, -1)
+    mean = ((x2 * m2).sum(2) / mm[:, None]).mean(0)
+    var = ((((x2 - mean[None, :, None]) ** 2) * m2).sum(2) / mm[:, None]).mean(0)
+    assert _rel(m.running_mean, 0.1 * torch.zeros(c, dtype=torch.float64) + 0.9 * mean) < RTOL
+    assert _rel(m.running_var, 0.1 * torch.ones(c, dtype=torch.float64) + 0.9 * var) < RTOL
+    # deterministic: a second call gives bit-identical results
+    m2_ = maskBN(c).to(cuda).train()
+    m2_.load_state_dict({k_: v_ for k_, v_ in m.state_dict().items()})
+    assert torch.equal(m2_(x.to(cuda), mask.to(cuda)).detach(), m2_(x.to(cuda), mask.to(cuda)).detach())
