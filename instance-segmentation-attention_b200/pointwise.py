@@ -280,7 +280,7 @@ class _MaxPool2x2Fn(torch.autograd.Function):
     def forward(ctx, x, with_skip):
         lib = _lib.load()
         N, C, H, W = x.shape
-        y = torch.empty(N, C, H // 2, W // 2, device=x.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+        y = torch.empty(N, C, H // 2, W // 2, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
         need = ctx.needs_input_grad[0]
         idx = torch.empty(N, H // 2, W // 2, C, device=x.device, dtype=torch.uint8) if need else None
         rc = lib.isa_maxpool2x2_fwd(x.data_ptr(), N, H, W, C, y.data_ptr(), _lib.ptr(idx), _lib.stream_ptr(x.device))
@@ -298,7 +298,7 @@ class _MaxPool2x2Fn(torch.autograd.Function):
         lib = _lib.load()
         N, C, H, W = ctx.geom
         idx, = ctx.saved_tensors
-        gx = torch.empty(N, C, H, W, device=idx.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+        gx = torch.empty(N, C, H, W, device=idx.device, dtype=torch.float32, memory_format=torch.channels_last)
         if gy is None:                       # only the skip was used downstream
             gx.copy_(g_skip)
             return gx, None
