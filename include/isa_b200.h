@@ -110,7 +110,14 @@ int isa_label_fg_count(const unsigned char* labels, long long total, int K, unsi
  * seed_idx_out [n_init][k] (k-means++ picks, may be NULL),
  * info        [16] i32: status (0 ok, 1 n<k, 2 non-finite input), best restart, n, Lloyd (grid) iterations run;
  *             [4..9] a coarse phase profile of the persistent Lloyd kernel as seen by CTA 0, in microseconds:
- *             E-steps, barrier after them, centre updates, barrier after them, whole loop, tail (re-run, inertia, selection).
+ *             E-steps, barrier after them, centre updates, barrier after them, whole loop, tail (re-run, inertia, selection);
+ *             [10..15] the same for the seeding kernel: candidate search, candidate potentials, closest update, grid
+ *             barriers (microseconds), then the number of scan segments and 8192-element rounds of CTA 0's searches.
+ * k-means++ follows scikit-learn's float32 code path decision for decision (float64-upcast candidate distances,
+ * candidates by searchsorted on the SEQUENTIAL float32 cumulative sum, float32 potentials).  E-step: packed FP32
+ * (fma.rn.f32x2) or, from 33 centres on (C <= 32, k <= 128), tcgen05 MMAs as a filter with an exact pass for the pairs
+ * inside the error bound -- both bit-exact with the oracle.  Environment switches (experiments): ISA_KM_TC / ISA_KM_FFMA
+ * force the E-step variant, ISA_KM_PRIV, ISA_KM_FLOW, ISA_KM_PPT, ISA_KM_STREAMING select measured alternatives.
  */
 size_t isa_kmeans_workspace_bytes(int ld, int C, int k, int n_init);
 
