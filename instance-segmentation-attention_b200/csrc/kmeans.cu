@@ -72,6 +72,9 @@ struct KmWs {
   int* seed_idx;           // [R][k]
   long long* seed_tot;     // [R][kSeedMaxCtas] per-CTA totals of closest[] (fixed point)
   int* seed_cand;          // [R][kMaxL] candidate indices of the current step
+  float* ub;               // [R][ld] Hamerly bounds of the packed-FP32 E-step: upper bound of the distance to the assigned centre
+  float* lb;               // [R][ld] ... lower bound of the distance to every other centre
+  float* delta;            // [R][k]  how far the last update moved every centre (rounded up)
   unsigned char* Xa;       // tensor-core E-step: Xc as bf16 hi / lo UMMA operand tiles, [half-tile of 128 points][hi | lo][128 x KP]
   float* xn;               // [ld] |x|_2 of every centred point, rounded up (error bound of the tensor-core distances)
   size_t total_bytes;
@@ -107,7 +110,7 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.seed_pot = (long long*)take(8 * (size_t)k * R * kMaxL);
   w.gen = (unsigned*)take(4 * (size_t)R);
   w.done = (unsigned*)take(4 * (size_t)R);
-  w.seed_prof = (unsigned long long*)take(8 * 6);
+  w.seed_prof = (unsigned long long*)take(8 * 8);
   w.zero_bytes = off;
   w.mean = (float*)take(4 * (size_t)C);
   w.Xc = (float*)take(4 * (size_t)C * ld);
@@ -118,8 +121,11 @@ KmWs km_carve(void* base, int ld, int C, int k, int R) {
   w.seed_idx = (int*)take(4 * (size_t)R * k);
   w.seed_tot = (long long*)take(8 * (size_t)R * kSeedMaxCtas);
   w.seed_cand = (int*)take(4 * (size_t)R * kMaxL);
+  w.ub = (float*)take(4 * (size_t)R * ld);
+  w.lb = (float*)take(4 * (size_t)R * ld);
+  w.delta = (float*)take(4 * (size_t)R * k);
   w.Xa = (unsigned char*)take(km_tc_ok(C, k) ? (size_t)km_tc_halftiles(ld) * 128 * km_tc_kp(C) * 4 : 0);
-  w.xn = (float*)take(km_tc_ok(C, k) ? 4 * (size_t)ld : 0);
+  w.xn = (float*)take(4 * (size_t)ld);
   w.total_bytes = off;
   return w;
 }
@@ -237,6 +243,18 @@ __global__ void km_init_centers_kernel(const float* __restrict__ init, int R, in
   }
 }
 
+// |x|_2 of every centred point, rounded up (xn^2 >= |x|^2 >= 0.9997 xn^2): the error bounds of the E-step filters need it
+__global__ void km_prep_xn_kernel(const int* __restrict__ n_ptr, int ld, int C, KmWs ws) {
+  const int n = *n_ptr;
+  if (*ws.status) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  float nn = 0.f;
+  if (i < n)
+    for (int f = 0; f < C; ++f) { const float v = ws.Xc[(size_t)f * ld + i]; nn = __fmaf_rn(v, v, nn); }
+  ws.xn[i] = __fmul_rn(__fsqrt_rn(nn), 1.0001f);
+}
+
 // Tensor-core operand of the points: every centred row split into bf16 hi + lo (x = hi + lo to ~16 mantissa bits) and
 // written in the canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices), one block of [hi | lo] per 128 points,
 // so that a Lloyd work item of 256 points is ONE bulk copy.  Rows >= n and features >= C are zero.  Also |x|_2 (rounded up).
@@ -267,7 +285,6 @@ __global__ void km_prep_tc_kernel(const int* __restrict__ n_ptr, int ld, int C, 
     *reinterpret_cast<uint4*>(blk + off) = hi;
     *reinterpret_cast<uint4*>(blk + 128 * KP * 2 + off) = lo;
   }
-  if (row < ld) ws.xn[row] = __fmul_rn(__fsqrt_rn(nn), 1.0001f);
 }
 
 // ------------------------------------------------------------------ seeding
@@ -809,6 +826,7 @@ struct LloydParams {
   double* inertia_out;  // [R]
   int* n_iter_out;      // [R]
   int* info;            // [16] status, best restart, n, total Lloyd iterations, then CTA 0's phase profile in us
+  int bounds;           // packed-FP32 kernel: Hamerly bounds (skip the points whose label provably cannot change) from this Lloyd iteration on, 0 = never
   int priv;             // packed-FP32 kernel: accumulate the moved points of a CTA in shared memory (k*C int64 + k int)
 };
 
@@ -869,6 +887,40 @@ __device__ __forceinline__ void estep_tile(const float* __restrict__ Xc, int ld,
       if (j == 0 || v0 < bv[2 * pp]) { bv[2 * pp] = v0; lab[2 * pp] = j; }
       if (j == 0 || v1 < bv[2 * pp + 1]) { bv[2 * pp + 1] = v1; lab[2 * pp + 1] = j; }
     }
+  }
+}
+
+// Two points given by their global indices (-1: none) against the centres in shared memory, same arithmetic as
+// estep_tile; also returns the best and the second-best score of each point (for the Hamerly bounds).
+template <int CP>
+__device__ __forceinline__ void estep_pair(const float* __restrict__ Xc, int ld, int C, int k, int i0, int i1,
+                                           const float* __restrict__ s_cdup, const float* __restrict__ s_csq, int (&lab)[2],
+                                           float (&best)[2], float (&second)[2]) {
+  km_u64 xp[CP];
+#pragma unroll
+  for (int f = 0; f < CP; ++f) {
+    const float a = (f < C && i0 >= 0) ? Xc[(size_t)f * ld + i0] : 0.f;
+    const float b = (f < C && i1 >= 0) ? Xc[(size_t)f * ld + i1] : 0.f;
+    xp[f] = km_pack2(a, b);
+  }
+  lab[0] = lab[1] = 0;
+  best[0] = best[1] = 0.f;
+  second[0] = second[1] = 3.4e38f;
+  for (int j = 0; j < k; ++j) {
+    const float* __restrict__ c = s_cdup + (size_t)j * 2 * CP;
+    km_u64 dot = 0ull;
+#pragma unroll
+    for (int f2 = 0; f2 < CP; f2 += 2) {
+      const ulonglong2 cv = *reinterpret_cast<const ulonglong2*>(c + 2 * f2);
+      km_ffma2(dot, xp[f2], cv.x);
+      km_ffma2(dot, xp[f2 + 1], cv.y);
+    }
+    const float cs = s_csq[j];
+    float d0, d1;
+    km_unpack2(dot, d0, d1);
+    const float v0 = __fmaf_rn(-2.f, d0, cs), v1 = __fmaf_rn(-2.f, d1, cs);
+    if (j == 0 || v0 < best[0]) { if (j) second[0] = best[0]; best[0] = v0; lab[0] = j; } else if (v0 < second[0]) second[0] = v0;
+    if (j == 0 || v1 < best[1]) { if (j) second[1] = best[1]; best[1] = v1; lab[1] = j; } else if (v1 < second[1]) second[1] = v1;
   }
 }
 
@@ -1058,6 +1110,8 @@ __device__ void lloyd_update_restart(const LloydParams& prm, const KmScales& sc,
     float acc = 0.f;
     for (int f = 0; f < C; ++f) { const float t = __fsub_rn(s_new[j * CP + f], cen[(size_t)j * C + f]); acc = __fmaf_rn(t, t, acc); }
     s_csq[j] = __fsqrt_rn(acc);
+    // upper bound of the true move |c' - c| (the fp32 chain errs by < (C + 2) 2^-24 relative) for the E-step's bounds
+    ws.delta[(size_t)r * k + j] = __fadd_ru(__fmul_ru(s_csq[j], 1.0000153f), 1e-30f);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) cen[idx] = s_new[(idx / C) * CP + idx % C];
@@ -1128,6 +1182,8 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
   __shared__ unsigned s_namb, s_chg;
   __shared__ int s_batch_r[8];
   __shared__ int s_nmoved;
+  __shared__ int s_nneed;
+  __shared__ float s_delta[kMaxK + 2], s_bmisc[4];
   __shared__ int s_active[kMaxInit];
   __shared__ int s_nactive;
   __shared__ long long s_redll[kLloydThreads / 32];
@@ -1182,10 +1238,10 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
         load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP, s_cdup);
         cur = r;
       }
-      if (threadIdx.x == 0) s_nmoved = 0;
-      __syncthreads();
       unsigned char* labels = ws.labels + (size_t)r * ld;
       unsigned char* acct = ws.acct + (size_t)r * ld;
+      if (threadIdx.x == 0) s_nmoved = 0;
+      __syncthreads();
       // previous labels / accounted clusters are fetched before the distance loop so their latency hides behind it
       int lprev[kPPT], aprev[kPPT];
 #pragma unroll
@@ -1259,6 +1315,202 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
     }
     if (acc_dirty) flush_acc(cur);
    }
+  };
+
+  // ---- packed-FP32 E-step with Hamerly bounds (exact).  Per point and restart: U >= |x - c_a| (a = its label), L <= |x - c_j|
+  // for every other centre, both shifted by how far the last update moved the centres.  If U^2 + 2 E < L^2, E = bound of the
+  // fp32 score error (C + 4) 2^-23 (|c|^2 + 2 |x| |c|), the oracle's fp32 argmin is still a -- strictly, so the first-index
+  // tie rule never decides -- and the point is skipped (~80 % of the point visits on the benchmark image).  The bounds of
+  // ALL tiles of a CTA's range are tested first (independent loads in flight, next tile prefetched), the points that need
+  // their distances are compacted into ONE shared list over the tiles, and the FFMA2 loop runs densely over that list.
+  auto run_estep_bounds = [&](int mode) {
+    if constexpr (!TC && PPT == 2) {
+      constexpr int kCap = 2048;
+      __shared__ unsigned s_list[kCap];                 // global index of a point that needs its distances
+      __shared__ unsigned short s_prev[kCap];           // its previous label | accounted cluster << 8
+      __shared__ unsigned s_mv[kCap + 512];             // moved points: global index
+      __shared__ unsigned short s_mval[kCap + 512];     // ... old accounted cluster | new << 8
+      __shared__ int s_chg;
+      const int total = s_nactive * tiles;
+      const float gam = (float)(C + 4) * 0x1p-23f;
+      const int tid = threadIdx.x;
+      // (Handing out chunks of items through a global counter instead of static ranges was measured: the barrier wait
+      // drops from 2.7 to 1.5 ms but every chunk reloads its restart's centres and the loop gets slower, 9.6 vs 8.7 ms.)
+      const int it0 = (int)((long long)blockIdx.x * total / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+      if (tid == 0) { s_nneed = 0; s_nmoved = 0; s_chg = 0; }
+      __syncthreads();
+      {
+       int item = it0;
+       while (item < it1) {
+        const int r = s_active[item / tiles];
+        int run_end = (item / tiles + 1) * tiles;                        // items of this restart inside the range
+        if (run_end > it1) run_end = it1;
+        unsigned char* labels = ws.labels + (size_t)r * ld;
+        unsigned char* acct = ws.acct + (size_t)r * ld;
+        float* ub = ws.ub + (size_t)r * ld;
+        float* lb = ws.lb + (size_t)r * ld;
+        __syncthreads();
+        load_centers(ws.centers + (size_t)r * k * C, s_cent, s_csq, k, C, CP, s_cdup);
+        for (int j = tid; j < k; j += kLloydThreads) s_delta[j] = __ldcg(ws.delta + (size_t)r * k + j);
+        __syncthreads();
+        if (warp == 0) {
+          float dm = 0.f, cm = 0.f;
+          for (int j = lane; j < k; j += 32) { dm = fmaxf(dm, s_delta[j]); cm = fmaxf(cm, s_csq[j]); }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o)); cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o)); }
+          if (lane == 0) {
+            const float cm2 = __fmul_ru(cm, 1.00001f);
+            s_bmisc[0] = dm; s_bmisc[1] = cm2; s_bmisc[2] = __fsqrt_ru(cm2);
+          }
+        }
+        __syncthreads();
+        const float dmax = s_bmisc[0], cmax2 = s_bmisc[1], cmax = s_bmisc[2];
+
+        // distances of the listed points, their labels / bounds / moves, then the exact M-step of everything that moved
+        auto process_list = [&]() {
+          __syncthreads();
+          const int nl = s_nneed;
+          bool changed = false;
+          for (int base = 0; base < nl; base += 2 * kLloydThreads) {
+            if (base + warp * 64 >= nl) break;
+            const int e0 = base + 2 * tid, e1 = e0 + 1;
+            const int ig0 = e0 < nl ? (int)s_list[e0] : -1, ig1 = e1 < nl ? (int)s_list[e1] : -1;
+            int lab2[2];
+            float best[2], second[2];
+            estep_pair<CP>(Xc, ld, C, k, ig0, ig1, s_cdup, s_csq, lab2, best, second);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int ig = q == 0 ? ig0 : ig1;
+              bool moved = false;
+              int a = 255;
+              const int l = lab2[q];
+              if (ig >= 0) {
+                const unsigned pv = s_prev[q == 0 ? e0 : e1];
+                const int lp = pv & 255;
+                a = pv >> 8;
+                if (mode == 0) {
+                  const float xnv = ws.xn[ig];
+                  const float xx_up = __fmul_ru(xnv, xnv), xx_lo = __fmul_rd(__fmul_rd(xnv, xnv), 0.9997f);
+                  const float E = __fmaf_ru(xx_up, 0x1p-17f, __fmul_ru(gam, __fmaf_ru(__fmul_ru(2.f, xnv), cmax, cmax2)));
+                  const float tu = __fadd_ru(__fadd_ru(xx_up, best[q]), E);
+                  float L = 3.0e38f;
+                  if (second[q] < 3.0e38f) {
+                    const float tlo = __fsub_rd(__fadd_rd(xx_lo, second[q]), E);
+                    L = tlo > 0.f ? __fsqrt_rd(tlo) : 0.f;
+                  }
+                  ub[ig] = tu > 0.f ? __fsqrt_ru(tu) : 0.f;
+                  lb[ig] = L;
+                  moved = (l != a);
+                  if (moved) acct[ig] = (unsigned char)l;
+                }
+                if (l != lp) { labels[ig] = (unsigned char)l; changed = true; }
+              }
+              const unsigned bal = __ballot_sync(0xffffffffu, moved);
+              if (bal) {
+                int mb = 0;
+                if (lane == 0) mb = atomicAdd(&s_nmoved, __popc(bal));
+                mb = __shfl_sync(0xffffffffu, mb, 0);
+                if (moved) {
+                  const int slot = mb + __popc(bal & ((1u << lane) - 1u));
+                  s_mv[slot] = (unsigned)ig;
+                  s_mval[slot] = (unsigned short)(a | (l << 8));
+                }
+              }
+            }
+          }
+          if (__any_sync(0xffffffffu, changed) && lane == 0) s_chg = 1;
+          __syncthreads();
+          if (mode == 0) {
+            if (s_chg && tid == 0) ws.changed[r] = 1;
+            const int nm = s_nmoved;
+            long long* gs = ws.sums + (size_t)r * k * C;
+            int* gcnt = ws.cnt + (size_t)r * k;
+            for (int idx = tid; idx < nm * C; idx += kLloydThreads) {
+              const int e = idx / C, f = idx - e * C;
+              const int ig = (int)s_mv[e];
+              const int a = s_mval[e] & 255, l = s_mval[e] >> 8;
+              const long long qv = to_fixed(Xc[(size_t)f * ld + ig], sc.p_x);
+              if (a != 255) atomicAdd((unsigned long long*)(gs + a * C + f), (unsigned long long)(-qv));
+              atomicAdd((unsigned long long*)(gs + l * C + f), (unsigned long long)qv);
+              if (f == 0) {
+                if (a != 255) atomicSub(gcnt + a, 1);
+                atomicAdd(gcnt + l, 1);
+              }
+            }
+          }
+          __syncthreads();
+          if (tid == 0) { s_nneed = 0; s_nmoved = 0; s_chg = 0; }
+          __syncthreads();
+        };
+
+        // ---- bound tests of the run's tiles (the next tile's values are fetched while this one is tested)
+        int lpv[2], apv[2];
+        float ubv[2], lbv[2], xnv[2];
+        auto fetch = [&](int tile) {
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int i = tile * kTile + p * kLloydThreads + tid;
+            lpv[p] = 255; apv[p] = 255; ubv[p] = 0.f; lbv[p] = 0.f; xnv[p] = 0.f;
+            if (i < n) {
+              lpv[p] = labels[i];
+              if (mode == 0) { apv[p] = acct[i]; ubv[p] = ub[i]; lbv[p] = lb[i]; xnv[p] = ws.xn[i]; }
+            }
+          }
+        };
+        fetch(item % tiles);
+        for (; item < run_end; ++item) {
+          const int tile = item % tiles;
+          __syncthreads();                                                // every append of the previous tile is done
+          // ONE decision for the CTA (a warp that raced ahead and appended must not change what a slower warp reads)
+          if (__syncthreads_or(tid == 0 && s_nneed + kTile > kCap)) process_list();
+          int lp[2], ap[2];
+          float u_[2], l_[2], x_[2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) { lp[p] = lpv[p]; ap[p] = apv[p]; u_[p] = ubv[p]; l_[p] = lbv[p]; x_[p] = xnv[p]; }
+          if (item + 1 < run_end) fetch((item + 1) % tiles);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int i = tile * kTile + p * kLloydThreads + tid;
+            bool need = i < n, moved = false;
+            if (need && mode == 0 && lp[p] != 255) {
+              const float U = __fadd_ru(u_[p], s_delta[lp[p]]);
+              const float L = fmaxf(__fsub_rd(l_[p], dmax), 0.f);
+              const float E = __fmul_ru(gam, __fmaf_ru(__fmul_ru(2.f, x_[p]), cmax, cmax2));
+              if (__fmaf_ru(U, U, __fmul_ru(2.0001f, E)) < __fmul_rd(L, L)) {
+                need = false;
+                ub[i] = U; lb[i] = L;
+                moved = (lp[p] != ap[p]);                                 // a relocated point returns to its label's cluster
+                if (moved) acct[i] = (unsigned char)lp[p];
+              }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (bal) {
+              int nb = 0;
+              if (lane == 0) nb = atomicAdd(&s_nneed, __popc(bal));
+              nb = __shfl_sync(0xffffffffu, nb, 0);
+              if (need) {
+                const int slot = nb + __popc(bal & ((1u << lane) - 1u));
+                s_list[slot] = (unsigned)i;
+                s_prev[slot] = (unsigned short)(lp[p] | (ap[p] << 8));
+              }
+            }
+            const unsigned balm = __ballot_sync(0xffffffffu, moved);
+            if (balm) {
+              int mb = 0;
+              if (lane == 0) mb = atomicAdd(&s_nmoved, __popc(balm));
+              mb = __shfl_sync(0xffffffffu, mb, 0);
+              if (moved) {
+                const int slot = mb + __popc(balm & ((1u << lane) - 1u));
+                s_mv[slot] = (unsigned)i;
+                s_mval[slot] = (unsigned short)(ap[p] | (lp[p] << 8));
+              }
+            }
+          }
+        }
+        process_list();
+       }
+      }
+    }
   };
 
   // ---- tensor-core E-step (TC): the distances of 256 points to the centres of up to `nb` restarts are ONE batch of
@@ -1523,10 +1775,13 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
     for (int idx = threadIdx.x; idx < k * C; idx += kLloydThreads) s_acc[idx] = 0;
     for (int j = threadIdx.x; j < k; j += kLloydThreads) s_acnt[j] = 0;
   }
+  for (int idx = blockIdx.x * kLloydThreads + threadIdx.x; idx < R * k; idx += gridDim.x * kLloydThreads) ws.delta[idx] = 0.f;
   // labels / acct start as "none" (255)
   for (size_t idx = (size_t)blockIdx.x * kLloydThreads + threadIdx.x; idx < (size_t)R * ld; idx += (size_t)gridDim.x * kLloydThreads) {
     ws.labels[idx] = 255;
     ws.acct[idx] = 255;
+    ws.ub[idx] = __int_as_float(0x7f800000);      // no bounds yet: the first E-step computes every point
+    ws.lb[idx] = 0.f;
   }
   grid_barrier(ws.barrier, epoch);
 
@@ -1539,7 +1794,9 @@ __global__ void __launch_bounds__(kLloydThreads, (PPT == 2 || TC) ? 2 : 1) km_ll
     rebuild_active(0);
     if (s_nactive == 0) break;
     ++total_iters;
-    if constexpr (TC) run_estep_tc(0); else run_estep(0);
+    // the bounds pay once most points have settled: the first iterations (nearly every point moves, the bounds are loose)
+    // take the plain path; the first bounded iteration starts from U = inf and computes every point
+    if constexpr (TC) run_estep_tc(0); else if (PPT == 2 && prm.bounds && it >= prm.bounds) run_estep_bounds(0); else run_estep(0);
     lap(t_e);
     grid_barrier(ws.barrier, epoch);
     lap(t_b1);
@@ -2068,8 +2325,17 @@ int launch_lloyd_ppt(const LloydParams& prm_in, int num_sms, cudaStream_t stream
   // 6.06 ms with direct RED.64s -- the reductions are not what the E-phase waits for; kept behind ISA_KM_PRIV=1.
   prm.priv = (getenv("ISA_KM_PRIV") && (smem + extra) * 2 <= 200 * 1024) ? 1 : 0;   // must not cost the second CTA per SM
   if (prm.priv) smem += extra;
+  // bounds from Lloyd iteration prm.bounds on (0 = never); ISA_KM_BOUNDS_FROM=<it> / ISA_KM_NOBOUNDS=1 for experiments.
+  // Measured on one B200 box, same process order (Lloyd loop of the four benchmark images, 49-52 k points, k = 16, 35
+  // restarts, 3100-3700 restart-iterations): 9.73 / 9.59 / 11.18 / 8.71 ms without, 8.43 / 8.91 / 10.50 / 8.20 ms with bounds
+  // from iteration 32 (80 % of the point visits skipped; what is left is the wait for the slowest CTA, whose range
+  // holds the restarts that still move).  Planted clusters that converge in ~50 iterations: 9.26 -> 9.59 ms (49 k points),
+  // 17.0 -> 17.5 ms (131 k): the bound arrays and the list passes cost 3 % there.  From iteration 1 / 6 / 16 the planted
+  // cases lose 10 / 8 / 4 % (loose bounds while every centre still moves) and the benchmark images gain no more.
+  prm.bounds = (PPT == 2 && !getenv("ISA_KM_NOBOUNDS")) ? (getenv("ISA_KM_BOUNDS_FROM") ? atoi(getenv("ISA_KM_BOUNDS_FROM")) : 32) : 0;
+  if (prm.bounds < 0) prm.bounds = 0;
   const void* fn = (const void*)km_lloyd_kernel<CP, PPT, false>;
-  if (smem > 48 * 1024) ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
   int occ = 0;
   ISA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLloydThreads, smem));
   ISA_CHECK_ARG(occ >= 1, "kmeans: Lloyd kernel does not fit on an SM (smem %zu)", smem);
@@ -2173,6 +2439,7 @@ int isa_kmeans_fit(const float* X, const int* n_ptr, int ld, int C, int k, int n
   km_prep_max_kernel<<<grid, 256, 0, stream>>>(X, n_ptr, ld, C, k, ws);
   km_prep_sums_kernel<<<grid, 256, 0, stream>>>(X, n_ptr, ld, C, ws);
   km_prep_center_kernel<<<grid, 256, 0, stream>>>(X, n_ptr, ld, C, ws);
+  km_prep_xn_kernel<<<(ld + 255) / 256, 256, 0, stream>>>(n_ptr, ld, C, ws);
   ISA_CUDA(cudaGetLastError());
   const int CP = pick_cp(C);
   if (init_centers) {
@@ -2191,7 +2458,7 @@ int isa_kmeans_fit(const float* X, const int* n_ptr, int ld, int C, int k, int n
   LloydParams prm;
   prm.n_ptr = n_ptr; prm.ld = ld; prm.C = C; prm.k = k; prm.R = n_init; prm.max_iter = max_iter; prm.tol_rel = tol_rel;
   prm.ws = ws; prm.labels_out = labels_out; prm.centers_out = centers_out; prm.inertia_out = inertia_out;
-  prm.n_iter_out = n_iter_out; prm.info = info; prm.priv = 0;
+  prm.n_iter_out = n_iter_out; prm.info = info; prm.priv = 0; prm.bounds = 0;
   switch (CP) {
     case 8: rc = launch_lloyd<8>(prm, di.num_sms, stream); break;
     case 16: rc = launch_lloyd<16>(prm, di.num_sms, stream); break;
