@@ -19,6 +19,8 @@ parser.add_argument('--dataset', type=str, required=True, help='Name of the data
 parser.add_argument('--names', required=True, help='validation_image_paths.txt')
 parser.add_argument('--counts', required=True, help='number_of_instances.txt (name,count)')
 parser.add_argument('--gt_dir', required=True, help='directory with <name>_label.png and <name>_fg.png')
+parser.add_argument('--empty_as_zero', action='store_true', help='score an image without predicted / annotated instances SBD 0 '
+                    'instead of raising like the reference (evaluate.py:31-38)')
 
 if __name__ == '__main__':
     opt = parser.parse_args()
@@ -40,8 +42,13 @@ if __name__ == '__main__':
         fg_seg_gt = (fg_seg_gt == 1).astype('bool')
         fg_seg_pred = (fg_seg_pred == 255).astype('bool')
         if ins_seg_pred.max() == 0 or ins_seg_gt.max() == 0:
-            # no predicted (or no annotated) instance: the reference's np.max([]) raises here (evaluate.py:31-38); an image
-            # that could not be clustered (pred_list.py writes an empty mask for it) scores 0 instead of aborting the run
+            # no predicted (or no annotated) instance: the reference's np.max([]) raises here (evaluate.py:31-38) and so
+            # does this script; --empty_as_zero scores such an image 0 instead (pred_list.py --keep_going writes an empty
+            # mask for an image that could not be clustered) and says so
+            if not opt.empty_as_zero:
+                raise ValueError('zero-size array to reduction operation maximum which has no identity '
+                                 '(%s has no %s instance; --empty_as_zero scores it 0)' % (name, 'predicted' if ins_seg_pred.max() == 0 else 'annotated'))
+            print('no instance in %s: SBD 0 (--empty_as_zero)' % name)
             sbds.append(0.0)
         else:
             sbds.append(calc_sbd(ins_seg_gt, ins_seg_pred))
