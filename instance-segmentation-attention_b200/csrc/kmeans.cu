@@ -700,7 +700,7 @@ km_seed_coop_kernel(const int* __restrict__ n_ptr, int ld, int C, int k, int L, 
       if (warp_ok)
         for (int r = 0; r < R; ++r) {
           const float cl = my_ok ? s_cl[r * kSeedThreads + threadIdx.x] : 0.f;
-#pragma unroll 2
+#pragma unroll 4
           for (int t = 0; t < L; ++t) {
             long long q = 0;
             if (my_ok) q = to_fixed(fminf(cl, sqdist_upcast<CP>(xr, xxr, s_cand + (size_t)(r * L + t) * CP, s_cc[r * L + t])), sc.p_d);
