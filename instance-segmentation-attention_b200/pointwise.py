@@ -13,6 +13,8 @@
         weight gradient (out x in = 24 x 24 from 65 536 rows) is a split-K batched GEMM instead of the single-CTA
         SIMT sgemm the library picks for that shape.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -62,6 +64,42 @@ class _BiasActFn(torch.autograd.Function):
         return gx, db, None
 
 
+class _ConvBiasReluFn(torch.autograd.Function):
+    """relu(conv2d(x, w) + b) with the bias + ReLU inside cuDNN's convolution epilogue (forward: no pass over the output
+    at all, bit-identical to the convolution followed by the in-place epilogue kernel, measured on B200: 3x3 convolutions
+    of the backbone 129-145 us fused against 218-220 us unfused at 16 x 64 x 256^2); backward: the single-pass
+    masked-gradient + bias-gradient kernel (isa_bias_act_bwd) in front of the library's convolution backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding, dilation, groups):
+        y = torch.cudnn_convolution_relu(x, w, b, stride, padding, dilation, groups)
+        ctx.conf = (stride, padding, dilation, groups)
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, w, y = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        if not y.is_contiguous(memory_format=torch.channels_last):
+            gm = gy * (y > 0)
+            db = gm.sum((0, 2, 3))
+        else:
+            rows, C = _rows_c(y)
+            gy = gy.contiguous(memory_format=torch.channels_last)
+            db = torch.empty(C, device=gy.device, dtype=torch.float32)
+            wsb = lib.isa_bias_act_workspace_bytes(C)
+            ws = torch.empty(wsb, device=gy.device, dtype=torch.uint8)
+            gm = torch.empty_like(gy)
+            rc = lib.isa_bias_act_bwd(gy.data_ptr(), y.data_ptr(), gm.data_ptr(), db.data_ptr(), rows, C, 1, ws.data_ptr(), wsb,
+                                      _lib.stream_ptr(gy.device))
+            _lib.check(rc, "isa_bias_act_bwd")
+        gx, gw, _ = torch.ops.aten.convolution_backward(gm, x, w, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return gx, gw, db, None, None, None, None
+
+
 def bias_act_(y, bias, relu):
     """y <- act(y + bias[channel]) in place (y: fresh convolution output, NHWC-dense or (..., C) contiguous)."""
     _lib.require_cuda(y, "activation")
@@ -81,6 +119,10 @@ class ConvBiasAct(nn.Conv2d):
         self.relu = relu
 
     def forward(self, x):
+        if (self.relu and self.bias is not None and x.is_cuda and x.dtype == torch.float32 and self.padding_mode == 'zeros'
+                and not isinstance(self.padding, str) and self.weight.shape[0] <= 256
+                and x.is_contiguous(memory_format=torch.channels_last) and os.environ.get("ISA_CONV_EPILOGUE") != "kernel"):
+            return _ConvBiasReluFn.apply(x, self.weight, self.bias, tuple(self.stride), tuple(self.padding), tuple(self.dilation), self.groups)
         y = self._conv_forward(x, self.weight, None)
         if self.bias is None:
             return F.relu(y) if self.relu else y

@@ -52,6 +52,30 @@ def test_conv_modules_match_stock_layers(cuda):
         torch.testing.assert_close(ours.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-3)
 
 
+def test_conv_epilogue_in_cudnn_equals_epilogue_kernel(cuda, monkeypatch):
+    """relu(conv + bias) with the epilogue inside cuDNN's convolution (default) against the bias-free convolution followed
+    by the in-place epilogue kernel (ISA_CONV_EPILOGUE=kernel): same output bit for bit, same gradients."""
+    from isa_b200.pointwise import ConvBiasAct
+    torch.manual_seed(5)
+    m = ConvBiasAct(16, 32, 3, padding=1, relu=True).to(cuda)
+    x = torch.randn(3, 16, 40, 28, device=cuda).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(3, 32, 40, 28, device=cuda).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for mode in (None, "kernel"):
+        if mode:
+            monkeypatch.setenv("ISA_CONV_EPILOGUE", mode)
+        else:
+            monkeypatch.delenv("ISA_CONV_EPILOGUE", raising=False)
+        m.zero_grad()
+        xa = x.clone().requires_grad_(True)
+        y = m(xa)
+        y.backward(g)
+        outs.append((y.detach().clone(), xa.grad.clone(), m.weight.grad.clone(), m.bias.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("rows,C", [(1000, 24), (65536, 24), (257, 8), (300, 64), (77, 40)])
 def test_add_layernorm_matches_torch(cuda, rows, C):
     from isa_b200.pointwise import add_layer_norm
