@@ -64,6 +64,26 @@ def test_network_embeddings_bit_exact_and_sklearn_golden(cuda, golden_dir, case)
     assert KM.same_up_to_permutation(labels, g[name + "_sk_labels"])
 
 
+@pytest.mark.parametrize("env", ["ISA_KM_TC=1", "ISA_KM_NOBOUNDS=1", "ISA_KM_BOUNDS_FROM=1", "ISA_KM_BOUNDS_FROM=3", "ISA_KM_PRIV=1",
+                                 "ISA_KM_STREAMING=1"])
+def test_every_lloyd_variant_is_bit_exact(cuda, monkeypatch, env):
+    """The measured alternatives behind the environment switches (tensor-core filter at k = 16, no bounds, bounds from the
+    first iterations, privatised M-step, streaming seeding) all reproduce the oracle bit for bit on a near-tied network
+    embedding and on a planted case with few points per centre."""
+    key, val = env.split("=")
+    monkeypatch.setenv(key, val)
+    X = net_inputs("net0")
+    o = KM.kmeans_oracle(X, 16, seed=0, n_init=8)
+    labels, res = _gpu_fit(cuda, X, 16, seed=0, n_init=8)
+    _assert_same_as_oracle(labels, res, o)
+    rs = np.random.RandomState(1)
+    cent = rs.standard_normal((20, 12)) * 2
+    Y = (cent[rs.randint(0, 20, 3001)] + rs.standard_normal((3001, 12))).astype(np.float32)
+    o = KM.kmeans_oracle(Y, 40, seed=4, n_init=5)
+    labels, res = _gpu_fit(cuda, Y, 40, seed=4, n_init=5)
+    _assert_same_as_oracle(labels, res, o)
+
+
 def test_cumsum_search_edge_cases(cuda):
     """The parallel float32 running-sum search against the oracle's sequential loop on inputs that stress it: exact ties
     (dyadic coordinates), long runs of zero distances (duplicates of the first centre), a heavy tail, a point count that
