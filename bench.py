@@ -200,11 +200,11 @@ def _timed_plain(torch):
 
 
 # ---------------------------------------------------------------------------------------------- clustering parity
-def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=150.0):
+def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=100.0, oracle_images=2):
     """Parity of the device clustering on the benchmark images, outside the timed region: bit-exact against the oracle
     (oracle/kmeans_oracle.c), against the real scikit-learn (labels up to permutation, SBD / |DiC| of the masks through
     metrics.calc_sbd / calc_dic), and -- where scikit-learn differs -- how stable scikit-learn itself is on that image
-    (1 thread vs all threads; inputs moved by one ulp): its fp32 BLAS sums depend on the thread count, so on near-tied
+    (1 thread vs all threads; feature columns reversed): its fp32 BLAS sums depend on the thread count, so on near-tied
     random-init embeddings its own answer is not unique."""
     from oracle import kmeans as KM
     from isa_b200 import metrics
@@ -217,12 +217,14 @@ def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=150.0
         fg, X = KM.gather_foreground(sem[0].cpu().numpy(), emb[0].cpu().numpy())
         if len(X) < k:
             continue
-        o = KM.kmeans_oracle(X, k, seed=0)
         got = pred.cluster_device(sem[0], emb[0], k)[1].cpu().numpy()
         ours = got[fg != 0]
+        # the C oracle takes ~12 s of host time per image: bit-exactness is re-checked on the first images only (the GPU
+        # tests assert it on every shape); None = not checked on this image
+        o = KM.kmeans_oracle(X, k, seed=0) if ti < oracle_images else None
         sk = KM.sklearn_fit_predict(X, k, 0)
         sk_mask = KM.scatter_labels(fg, sk)
-        rec = {"identical_to_oracle": bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"]))),
+        rec = {"identical_to_oracle": bool(np.array_equal(got, KM.scatter_labels(fg, o["labels"]))) if o is not None else None,
                "identical_to_sklearn": bool(KM.same_up_to_permutation(ours, sk + 1)),
                "agreement_with_sklearn": round(float(KM.partition_agreement(ours, sk + 1)), 5),
                "sbd_ours_vs_sklearn_masks": round(float(metrics.calc_sbd(sk_mask, got)), 5),
@@ -239,8 +241,6 @@ def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=150.0
                     sk1 = KM.sklearn_fit_predict(X, k, 0)
                 rec["sklearn_self_agreement_1_vs_all_threads"] = round(float(KM.partition_agreement(sk1, sk)), 5)
                 rec["sbd_sklearn_1thread_vs_all_threads_masks"] = round(float(metrics.calc_sbd(sk_mask, KM.scatter_labels(fg, sk1))), 5)
-                skp = KM.sklearn_fit_predict(np.nextafter(X, np.float32(np.inf)).astype(np.float32), k, 0)
-                rec["sklearn_self_agreement_inputs_plus_1ulp"] = round(float(KM.partition_agreement(skp, sk)), 5)
                 # the same points with the feature columns reversed: the identical problem in exact arithmetic (every
                 # distance, mean and the k-means++ stream are unchanged), only the fp32 summation order differs
                 skr = KM.sklearn_fit_predict(np.ascontiguousarray(X[:, ::-1]), k, 0)
@@ -250,11 +250,12 @@ def clustering_parity(pred, model, tens, k, raw_hw, max_images=4, budget_s=150.0
                 rec["sklearn_self_agreement_error"] = repr(e)
         per_image.append(rec)
     flags = {"images_checked": len(per_image),
-             "labels_identical_to_oracle": bool(per_image) and all(r["identical_to_oracle"] for r in per_image),
+             "labels_identical_to_oracle": bool(per_image) and all(r["identical_to_oracle"] for r in per_image if r["identical_to_oracle"] is not None),
+             "images_checked_against_oracle": int(sum(1 for r in per_image if r["identical_to_oracle"] is not None)),
              "images_identical_to_sklearn": int(sum(r["identical_to_sklearn"] for r in per_image)),
              "labels_identical_to_sklearn_up_to_permutation": bool(per_image) and all(r["identical_to_sklearn"] for r in per_image),
              "images_where_sklearn_disagrees_with_itself": int(sum(1 for r in per_image if min(
-                 r.get("sklearn_self_agreement_1_vs_all_threads", 1.0), r.get("sklearn_self_agreement_inputs_plus_1ulp", 1.0),
+                 r.get("sklearn_self_agreement_1_vs_all_threads", 1.0),
                  r.get("sklearn_self_agreement_feature_order_reversed", 1.0)) < 1.0)),
              "sklearn_partition_agreement": min([r["agreement_with_sklearn"] for r in per_image]) if per_image else None,
              "per_image": per_image}
